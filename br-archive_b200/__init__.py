@@ -1,0 +1,247 @@
+"""br-archive_b200 -- B200-native block-compression path of BR-Archive (CRC32C, BWT, MTF, RLE, Huffman).
+
+The product is the C-ABI shared library ``libbra_b200.so`` built from ``csrc/`` (hand-written
+sm_100a CUDA kernels, declared in ``include/*.h``). This Python module is only the thin ctypes
+binding the tests and ``bench.py`` use; torch appears here purely for device memory and streams.
+
+There is no CPU fallback: importing works without a GPU (so the CPU test-suite can check that
+the library loads and exports its symbols), but every compute entry point needs a CUDA device,
+and a missing ``libbra_b200.so`` raises immediately.
+
+The directory name contains a hyphen, so import it through ``bra_pkg.load()`` (repo root),
+which registers it as ``br_archive_b200``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libbra_b200.so")
+HOSTLOGIC_PATH = os.path.join(HERE, "libbra_hostlogic.so")
+
+HDR_BYTES = 268
+DISK_HDR_BYTES = 267
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+
+# every symbol include/*.h declares; tests/test_abi.py checks the library exports them all
+REFERENCE_API = [
+    "bra_bwt_encode", "bra_bwt_encode2", "bra_bwt_decode", "bra_bwt_decode2",
+    "bra_mtf_encode", "bra_mtf_encode2", "bra_mtf_decode", "bra_mtf_decode2",
+    "bra_rle_encode", "bra_rle_decode_compute_size", "bra_rle_decode",
+    "bra_huffman_encode", "bra_huffman_decode", "bra_huffman_chunk_free",
+    "bra_crc32c", "bra_crc32c_table", "bra_crc32c_sse42", "bra_crc32c_combine", "bra_crc32c_use_sse42",
+    "bra_init", "bra_quit", "bra_has_sse42",
+]
+BATCH_API = [
+    "bra_b200_device_count", "bra_b200_ctx_create", "bra_b200_ctx_destroy", "bra_b200_block_size", "bra_b200_max_batch",
+    "bra_b200_payload_stride", "bra_b200_workspace_bytes", "bra_b200_last_stats", "bra_b200_encode_device", "bra_b200_decode_device",
+    "bra_b200_encode_bound", "bra_b200_encode_host", "bra_b200_decode_host", "bra_b200_gen_random", "bra_b200_gen_text",
+    "bra_b200_gen_periodic", "bra_b200_prof_enable", "bra_b200_prof_reset", "bra_b200_prof_count", "bra_b200_prof_read",
+]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into libbra_b200.so (nvcc cross-compiles without a GPU)."""
+    out = None if verbose else subprocess.DEVNULL
+    subprocess.check_call(["make", "-C", HERE, "-j8", "all"], stdout=out)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The product library. Raises if it has not been built: nothing here falls back to the CPU."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the compression path)")
+    L = C.CDLL(LIB_PATH)
+    L.bra_b200_device_count.restype = C.c_int
+    L.bra_b200_ctx_create.restype = C.c_void_p
+    L.bra_b200_ctx_create.argtypes = [C.c_int, C.c_uint32, C.c_uint32]
+    L.bra_b200_ctx_destroy.argtypes = [C.c_void_p]
+    L.bra_b200_block_size.restype = C.c_uint32
+    L.bra_b200_block_size.argtypes = [C.c_void_p]
+    L.bra_b200_max_batch.restype = C.c_uint32
+    L.bra_b200_max_batch.argtypes = [C.c_void_p]
+    L.bra_b200_payload_stride.restype = C.c_uint64
+    L.bra_b200_payload_stride.argtypes = [C.c_void_p]
+    L.bra_b200_workspace_bytes.restype = C.c_uint64
+    L.bra_b200_workspace_bytes.argtypes = [C.c_void_p]
+    L.bra_b200_last_stats.argtypes = [C.c_void_p, u32p, u32p, C.POINTER(C.c_uint64)]
+    L.bra_b200_encode_device.restype = C.c_int
+    L.bra_b200_encode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bra_b200_decode_device.restype = C.c_int
+    L.bra_b200_decode_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]
+    L.bra_b200_encode_bound.restype = C.c_uint64
+    L.bra_b200_encode_bound.argtypes = [C.c_void_p, C.c_uint64]
+    L.bra_b200_encode_host.restype = C.c_int
+    L.bra_b200_encode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), u32p]
+    L.bra_b200_decode_host.restype = C.c_int
+    L.bra_b200_decode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), u32p]
+    L.bra_b200_gen_random.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+    L.bra_b200_gen_text.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_char_p), C.c_uint32]
+    L.bra_b200_gen_periodic.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
+    L.bra_b200_prof_enable.argtypes = [C.c_int]
+    L.bra_b200_prof_count.restype = C.c_int
+    L.bra_b200_prof_read.restype = C.c_int
+    L.bra_b200_prof_read.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_uint64), C.POINTER(C.c_double)]
+    _lib = L
+    return L
+
+
+def prof_enable(timing: bool):
+    lib().bra_b200_prof_enable(1 if timing else 0)
+
+
+def prof_reset():
+    lib().bra_b200_prof_reset()
+
+
+def prof_read():
+    """-> {kernel family: (launches, accumulated device ms)}; ms is 0 unless timing was enabled."""
+    L = lib()
+    out = {}
+    for i in range(L.bra_b200_prof_count()):
+        name, n, ms = C.c_char_p(), C.c_uint64(0), C.c_double(0.0)
+        L.bra_b200_prof_read(i, C.byref(name), C.byref(n), C.byref(ms))
+        out[name.value.decode()] = (int(n.value), float(ms.value))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic workloads; numpy arrays in host memory
+# ---------------------------------------------------------------------------------------------
+def gen_random(n: int, seed: int = 2):
+    import numpy as np
+    out = np.empty(n, dtype=np.uint8)
+    lib().bra_b200_gen_random(out.ctypes.data, n, seed)
+    return out
+
+
+def gen_text(n: int, vocab, seed: int = 1):
+    import numpy as np
+    out = np.empty(n, dtype=np.uint8)
+    arr = (C.c_char_p * len(vocab))(*[v.encode("latin-1") for v in vocab])
+    lib().bra_b200_gen_text(out.ctypes.data, n, seed, arr, len(vocab))
+    return out
+
+
+def gen_periodic(n: int, pattern: bytes):
+    import numpy as np
+    out = np.empty(n, dtype=np.uint8)
+    pat = np.frombuffer(pattern, dtype=np.uint8)
+    lib().bra_b200_gen_periodic(out.ctypes.data, n, pat.ctypes.data, len(pattern))
+    return out
+
+
+class Context:
+    """One GPU context of the batched path (include/bra_b200.h). Tensors are torch CUDA uint8/int32."""
+
+    def __init__(self, device: int = 0, block_size: int = 1 << 20, max_batch: int = 256):
+        self.L = lib()
+        self.device = device
+        self.block_size = block_size
+        self.handle = self.L.bra_b200_ctx_create(device, block_size, max_batch)
+        if not self.handle:
+            raise RuntimeError("bra_b200_ctx_create failed (no CUDA device, or out of device memory); there is no CPU fallback")
+        self.payload_stride = int(self.L.bra_b200_payload_stride(self.handle))
+        self.max_batch = int(self.L.bra_b200_max_batch(self.handle))
+
+    def close(self):
+        if self.handle:
+            self.L.bra_b200_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stats(self):
+        r, s, l = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
+        self.L.bra_b200_last_stats(self.handle, C.byref(r), C.byref(s), C.byref(l))
+        return {"bwt_rounds": r.value, "huf_sweeps": s.value}
+
+    # ---- device-resident -------------------------------------------------------------------
+    def alloc_encode_outputs(self, nblk: int):
+        import torch
+        dev = torch.device("cuda", self.device)
+        return (torch.empty(nblk * HDR_BYTES, dtype=torch.uint8, device=dev),
+                torch.empty(nblk * self.payload_stride, dtype=torch.uint8, device=dev),
+                torch.empty(nblk, dtype=torch.int32, device=dev))
+
+    def alloc_decode_outputs(self, nblk: int):
+        import torch
+        dev = torch.device("cuda", self.device)
+        return (torch.empty(nblk * self.block_size, dtype=torch.uint8, device=dev),
+                torch.empty(nblk, dtype=torch.int32, device=dev),
+                torch.empty(nblk, dtype=torch.int32, device=dev),
+                torch.empty(nblk, dtype=torch.int32, device=dev))
+
+    def encode_device(self, d_in, total: int, outputs=None, stream=None):
+        """d_in: CUDA uint8 tensor holding `total` bytes. Returns (hdr, payload, crc_raw) tensors."""
+        import torch
+        nblk = (total + self.block_size - 1) // self.block_size
+        last = total - (nblk - 1) * self.block_size
+        if outputs is None:
+            outputs = self.alloc_encode_outputs(nblk)
+        hdr, pay, crc = outputs
+        st = (stream or torch.cuda.current_stream(self.device)).cuda_stream
+        rc = self.L.bra_b200_encode_device(self.handle, d_in.data_ptr(), nblk, last, hdr.data_ptr(), pay.data_ptr(), crc.data_ptr(), st)
+        if rc != 0:
+            raise RuntimeError(f"bra_b200_encode_device failed with code {rc}")
+        return hdr, pay, crc
+
+    def decode_device(self, hdr, pay, nblk: int, hint_r: int = 0, hint_c: int = 0, outputs=None, stream=None):
+        import torch
+        if outputs is None:
+            outputs = self.alloc_decode_outputs(nblk)
+        out, out_len, crc, status = outputs
+        st = (stream or torch.cuda.current_stream(self.device)).cuda_stream
+        rc = self.L.bra_b200_decode_device(self.handle, hdr.data_ptr(), pay.data_ptr(), nblk, hint_r, hint_c, out.data_ptr(),
+                                           out_len.data_ptr(), crc.data_ptr(), status.data_ptr(), st)
+        if rc != 0:
+            raise RuntimeError(f"bra_b200_decode_device failed with code {rc}")
+        return out, out_len, crc, status
+
+    # ---- host buffers (numpy uint8 arrays or pinned torch CPU tensors) ------------------------------
+    def encode_host(self, data, out=None, crc_chain: int = 0):
+        import numpy as np
+        n = int(data.nbytes) if hasattr(data, "nbytes") else int(data.numel())
+        ptr = data.ctypes.data if hasattr(data, "ctypes") else data.data_ptr()
+        bound = int(self.L.bra_b200_encode_bound(self.handle, n))
+        if out is None:
+            out = np.empty(bound, dtype=np.uint8)
+        optr = out.ctypes.data if hasattr(out, "ctypes") else out.data_ptr()
+        ocap = int(out.nbytes) if hasattr(out, "nbytes") else int(out.numel())
+        osz = C.c_uint64(0)
+        crc = C.c_uint32(crc_chain)
+        rc = self.L.bra_b200_encode_host(self.handle, ptr, n, optr, ocap, C.byref(osz), C.byref(crc))
+        if rc != 0:
+            raise RuntimeError(f"bra_b200_encode_host failed with code {rc}")
+        return out[: osz.value], int(crc.value)
+
+    def decode_host(self, stream_bytes, out_cap: int, out=None, crc_chain: int = 0):
+        import numpy as np
+        n = int(stream_bytes.nbytes) if hasattr(stream_bytes, "nbytes") else int(stream_bytes.numel())
+        ptr = stream_bytes.ctypes.data if hasattr(stream_bytes, "ctypes") else stream_bytes.data_ptr()
+        if out is None:
+            out = np.empty(max(out_cap, 1), dtype=np.uint8)
+        optr = out.ctypes.data if hasattr(out, "ctypes") else out.data_ptr()
+        osz = C.c_uint64(0)
+        crc = C.c_uint32(crc_chain)
+        rc = self.L.bra_b200_decode_host(self.handle, ptr, n, optr, out_cap, C.byref(osz), C.byref(crc))
+        if rc != 0:
+            raise RuntimeError(f"bra_b200_decode_host failed with code {rc}")
+        return out[: osz.value], int(crc.value)

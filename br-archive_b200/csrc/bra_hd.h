@@ -1,0 +1,261 @@
+// bra_hd.h -- scalar logic shared by host and device code (compiles with g++ and nvcc).
+//
+// Everything here is small, branchy, per-block work (a 256-symbol Huffman tree, CRC
+// polynomial arithmetic) that the kernels run on one thread/warp per block and that the
+// host-side C ABI needs as well. Keeping one definition lets the CPU test-suite exercise the
+// exact code the GPU executes.
+#pragma once
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BRA_HD __host__ __device__ __forceinline__
+#else
+#define BRA_HD static inline
+#endif
+
+#define BRA_ALPHABET 256
+#define BRA_CRC_POLY 0x82F63B78u   // reflected Castagnoli polynomial (reference src/utils/lib_bra_crc32c.c:26)
+#define BRA_HUF_MAXLEN_DEC 32      // longest code the decoder accepts (Huffman)
+
+// ---------------------------------------------------------------------------------------
+// GF(2) polynomial arithmetic modulo the CRC-32C polynomial, reflected bit order
+// (bit 31 holds x^0). crc_shift(c, k) advances a CRC register over k zero bytes, i.e. it
+// multiplies by x^(8k) mod P -- the "fold" used to combine partial CRCs of adjacent pieces
+// (what reference lib_bra_crc32c.c:181-231 does with 32x32 bit-matrix squaring).
+// ---------------------------------------------------------------------------------------
+BRA_HD uint32_t bra_gf_mul(uint32_t a, uint32_t b)
+{
+    uint32_t acc = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 8
+#endif
+    for (int i = 0; i < 32; ++i)
+    {
+        acc ^= (0u - ((a >> (31 - i)) & 1u)) & b;
+        b = (b >> 1) ^ ((0u - (b & 1u)) & BRA_CRC_POLY);
+    }
+    return acc;
+}
+
+// x^(8*2^i) mod P for i = 0..39, filled by bra_gf_init_pow() (host) and copied to the device.
+struct bra_gf_pow_t
+{
+    uint32_t p2[40];
+};
+
+BRA_HD void bra_gf_init_pow(bra_gf_pow_t* t)
+{
+    uint32_t v = 0x00800000u;  // x^8
+    for (int i = 0; i < 40; ++i)
+    {
+        t->p2[i] = v;
+        v        = bra_gf_mul(v, v);
+    }
+}
+
+// x^(8*nbytes) mod P
+BRA_HD uint32_t bra_gf_xpow8(const bra_gf_pow_t* t, uint64_t nbytes)
+{
+    uint32_t r = 0x80000000u;  // x^0
+    for (int i = 0; nbytes != 0 && i < 40; ++i, nbytes >>= 1)
+        if (nbytes & 1u) r = bra_gf_mul(r, t->p2[i]);
+    return r;
+}
+
+// crc(A || B) from crc(A), crc(B), |B|  -- same contract as reference bra_crc32c_combine
+BRA_HD uint32_t bra_crc_combine(const bra_gf_pow_t* t, uint32_t crc_a, uint32_t crc_b, uint64_t len_b)
+{
+    if (len_b == 0) return crc_a;
+    return bra_gf_mul(crc_a, bra_gf_xpow8(t, len_b)) ^ crc_b;
+}
+
+// ---------------------------------------------------------------------------------------
+// Huffman code lengths: exact replay of the reference's sorted-list tree build
+// (reference src/encoders/bra_huffman.c:90-118 insert rule, :132-186 build, :188-220 depths).
+//
+// The reference keeps a singly linked list ascending by frequency. insert(x): x becomes the
+// head iff the list is empty or head.freq > x.freq; otherwise it is linked after the last
+// node, starting from the head, whose successor has freq < x.freq. On a sorted array that is
+//     pos = (a[0].freq > x.freq) ? 0 : max(1, #{j : a[j].freq < x.freq}).
+// The array is kept in a window [head, head+m) of a 512-slot buffer; popping the two minima
+// frees two slots in front, so the parent is inserted by shifting the (short) front part down.
+// ---------------------------------------------------------------------------------------
+struct bra_huf_build_ws_t
+{
+    uint32_t nfreq[512];   // node frequency (uint32 sums wrap like the reference)
+    uint16_t parent[512];  // parent node id
+    uint16_t list[768];    // sorted window of node ids
+    uint16_t leaf_of[256]; // node id of each present symbol
+};
+
+BRA_HD uint32_t bra_huf_insert_pos(const bra_huf_build_ws_t* ws, uint32_t head, uint32_t m, uint32_t f)
+{
+    if (m == 0 || ws->nfreq[ws->list[head]] > f) return 0;
+    // lower bound of f in the sorted window
+    uint32_t lo = 0, hi = m;
+    while (lo < hi)
+    {
+        uint32_t mid = (lo + hi) >> 1;
+        if (ws->nfreq[ws->list[head + mid]] < f)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo < 1 ? 1 : lo;
+}
+
+// Returns number of distinct symbols (0 => empty input, caller reports failure like the reference).
+BRA_HD uint32_t bra_huf_build_lengths(const uint32_t* freq, uint8_t* lengths, bra_huf_build_ws_t* ws)
+{
+    uint32_t nn = 0, m = 0;
+    uint32_t head = 256;  // window grows to the right during leaf insertion, moves right during merges
+    for (int s = 0; s < BRA_ALPHABET; ++s) lengths[s] = 0;
+    for (int s = 0; s < BRA_ALPHABET; ++s)
+    {
+        const uint32_t f = freq[s];
+        if (f == 0) continue;
+        const uint32_t id  = nn++;
+        ws->nfreq[id]      = f;
+        ws->leaf_of[id]    = (uint16_t) s;  // leaves get ids 0..k-1 in symbol order
+        const uint32_t pos = bra_huf_insert_pos(ws, head, m, f);
+        for (uint32_t j = m; j > pos; --j) ws->list[head + j] = ws->list[head + j - 1];
+        ws->list[head + pos] = (uint16_t) id;
+        ++m;
+    }
+    const uint32_t nleaves = nn;
+    if (nleaves == 0) return 0;
+    if (nleaves == 1)
+    {
+        lengths[ws->leaf_of[0]] = 1;  // lone leaf: length 1, code 0 (bra_huffman.c:201-207)
+        return 1;
+    }
+    while (m > 1)
+    {
+        const uint32_t l = ws->list[head], r = ws->list[head + 1];
+        head += 2;
+        m -= 2;
+        const uint32_t id = nn++;
+        const uint32_t f  = ws->nfreq[l] + ws->nfreq[r];
+        ws->nfreq[id]     = f;
+        ws->parent[l]     = (uint16_t) id;
+        ws->parent[r]     = (uint16_t) id;
+        const uint32_t pos = bra_huf_insert_pos(ws, head, m, f);
+        // shift the front part [0,pos) one slot down into the space freed by the pops
+        for (uint32_t j = 0; j < pos; ++j) ws->list[head - 1 + j] = ws->list[head + j];
+        head -= 1;
+        ws->list[head + pos] = (uint16_t) id;
+        ++m;
+    }
+    const uint32_t root = nn - 1;
+    for (uint32_t i = 0; i < nleaves; ++i)
+    {
+        uint32_t d = 0, v = i;
+        while (v != root)
+        {
+            v = ws->parent[v];
+            ++d;
+        }
+        lengths[ws->leaf_of[i]] = (uint8_t) d;
+    }
+    return nleaves;
+}
+
+// Canonical code assignment, reference bra_huffman.c:227-261: a uint32 running code shifted once
+// per length 1..256 (so it wraps exactly like the reference beyond 32 bits); symbols ascending
+// within a length.
+BRA_HD void bra_huf_canonical(const uint8_t* lengths, uint32_t* codes)
+{
+    uint32_t count[257];
+    for (int i = 0; i <= 256; ++i) count[i] = 0;
+    for (int i = 0; i < 256; ++i)
+        if (lengths[i]) ++count[lengths[i]];
+    uint32_t code = 0;
+    for (int len = 1; len <= 256; ++len)
+    {
+        code <<= 1;
+        const uint32_t c = count[len];
+        count[len]       = code;
+        code += c;
+    }
+    for (int i = 0; i < 256; ++i) codes[i] = lengths[i] ? count[lengths[i]]++ : 0u;
+}
+
+// ---------------------------------------------------------------------------------------
+// Canonical decode tables (valid prefix codes with lengths <= BRA_HUF_MAXLEN_DEC).
+// For a left-aligned 32-bit window w, the code length is the smallest L with
+// w < limit[L]  (limit is 33-bit, hence uint64), and the symbol is
+// sorted_sym[base[L] + (w >> (32-L)) - first[L]].
+// Returns false when the lengths are not a usable prefix code (oversubscribed Kraft sum or a
+// length above the supported maximum); the reference fails such headers at tree rebuild
+// (bra_huffman.c:294-303) or later at the bit walk.
+// ---------------------------------------------------------------------------------------
+struct bra_huf_dec_t
+{
+    uint64_t limit[BRA_HUF_MAXLEN_DEC + 2]; // limit[L], L = 1..32; limit[0] = 0
+    uint32_t first[BRA_HUF_MAXLEN_DEC + 2]; // first canonical code of length L
+    uint16_t base[BRA_HUF_MAXLEN_DEC + 2];  // index of first symbol of length L in sorted_sym
+    uint16_t count[BRA_HUF_MAXLEN_DEC + 2];
+    uint8_t  sorted_sym[256];
+    uint32_t min_len, max_len, nsym;
+};
+
+BRA_HD bool bra_huf_make_dec(const uint8_t* lengths, bra_huf_dec_t* d)
+{
+    for (int i = 0; i < BRA_HUF_MAXLEN_DEC + 2; ++i)
+    {
+        d->count[i] = 0;
+        d->limit[i] = 0;
+        d->first[i] = 0;
+        d->base[i]  = 0;
+    }
+    d->min_len = 0;
+    d->max_len = 0;
+    d->nsym    = 0;
+    for (int s = 0; s < 256; ++s)
+    {
+        const uint32_t l = lengths[s];
+        if (l == 0) continue;
+        if (l > BRA_HUF_MAXLEN_DEC) return false;
+        d->count[l]++;
+        d->nsym++;
+        if (d->min_len == 0 || l < d->min_len) d->min_len = l;
+        if (l > d->max_len) d->max_len = l;
+    }
+    if (d->nsym == 0) return true;  // empty tree: every bit is an invalid code (max_len == 0)
+    uint64_t code = 0;
+    uint32_t idx  = 0;
+    for (uint32_t l = 1; l <= BRA_HUF_MAXLEN_DEC; ++l)
+    {
+        code <<= 1;
+        d->first[l] = (uint32_t) code;
+        d->base[l]  = (uint16_t) idx;
+        code += d->count[l];
+        idx += d->count[l];
+        if (code > (1ull << l)) return false;  // Kraft sum above 1: codes would collide
+        d->limit[l] = code << (32 - l);
+    }
+    uint16_t next[BRA_HUF_MAXLEN_DEC + 2];
+    for (int i = 0; i < BRA_HUF_MAXLEN_DEC + 2; ++i) next[i] = d->base[i];
+    for (int s = 0; s < 256; ++s)
+        if (lengths[s]) d->sorted_sym[next[lengths[s]]++] = (uint8_t) s;
+    return true;
+}
+
+// Decode one symbol from the left-aligned 32-bit window. Returns the code length, 0 if no
+// codeword matches (the reference's "invalid code sequence", bra_huffman.c:466-470).
+BRA_HD uint32_t bra_huf_decode_one(const bra_huf_dec_t* d, uint32_t w, uint8_t* sym)
+{
+    for (uint32_t l = d->min_len; l <= d->max_len; ++l)
+    {
+        if ((uint64_t) w < d->limit[l])
+        {
+            // w >= limit[l-1] here, so the prefix is a real code of length l iff count[l] > 0
+            const uint32_t c = w >> (32 - l);
+            if (c < d->first[l]) return 0;
+            *sym = d->sorted_sym[d->base[l] + (c - d->first[l])];
+            return l;
+        }
+    }
+    return 0;
+}

@@ -1,0 +1,175 @@
+// bra_kernels.h -- internal launchers shared between the .cu files (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "bra_hd.h"
+
+namespace bra {
+
+// ---- prof.cu: launch accounting (see include/bra_b200.h, bra_b200_prof_*) ------------------------
+enum ProfId
+{
+    P_CRC, P_RS_HIST, P_RS_SCAN, P_RS_SCATTER, P_BWT_PERIOD, P_BWT_KEYS, P_BWT_HEADS, P_BWT_RANKS, P_BWT_PREPARE, P_BWT_GATHER, P_BWT_MISC,
+    P_MTF_SUMMARY, P_MTF_SCAN, P_MTF_APPLY, P_RLE_ENC_HEADS, P_RLE_ENC_LIT, P_RLE_ENC_SIZE, P_RLE_ENC_EMIT, P_RLE_DEC_EXIT, P_RLE_DEC_CHAIN,
+    P_RLE_DEC_MARK, P_RLE_DEC_EXPAND, P_HUF_HIST, P_HUF_BUILD, P_HUF_BITS, P_HUF_PACK, P_HUF_DEC_TABLES, P_HUF_DEC_SYNC, P_HUF_DEC_SCAN,
+    P_HUF_DEC_WRITE, P_HUF_DEC_TRAILING, P_IBWT_WALK_LEN, P_IBWT_STITCH, P_IBWT_WALK_EMIT, P_GLUE, P_COUNT
+};
+void prof_pre(int id, cudaStream_t st);
+void prof_post(int id, cudaStream_t st);
+// every kernel launch of the library goes through this macro
+#define BRA_LAUNCH(id, st, ...)  \
+    do                           \
+    {                            \
+        bra::prof_pre(id, st);   \
+        __VA_ARGS__;             \
+        bra::prof_post(id, st);  \
+    } while (0)
+
+// ---- crc32c.cu ----------------------------------------------------------------------------
+bool                crc_init_tables();
+const bra_gf_pow_t* crc_host_pow();
+// d_crc[b] = CRC-32C of block b continued from d_prev[b] (or 0). len from d_len[b] or fixed_len.
+bool crc_blocks(const uint8_t* d_in, uint64_t stride, const uint32_t* d_len, uint32_t fixed_len, uint32_t max_len, uint32_t nblk,
+                const uint32_t* d_prev, uint32_t* d_crc, cudaStream_t st);
+bool crc_headers(const uint8_t* d_hdr, uint32_t item_bytes, uint32_t nitems, uint32_t* d_out, cudaStream_t st);
+
+// ---- sort.cu ------------------------------------------------------------------------------
+size_t radix_hist_bytes(uint32_t max_len, uint32_t nblk);
+bool   radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t stride,
+                      const uint32_t* d_len, const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t* d_hist,
+                      cudaStream_t st);
+bool   radix_pass_u8_index_packed(const uint8_t* keys, uint32_t* packed_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len,
+                                  uint32_t nblk, uint32_t* d_hist, cudaStream_t st);
+bool   radix_pass_u8_index(const uint8_t* keys, uint32_t* vals_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len, uint32_t nblk,
+                           uint32_t* d_hist, cudaStream_t st);
+
+// ---- bwt.cu -------------------------------------------------------------------------------
+struct BwtFwdArgs
+{
+    const uint8_t*  d_in;
+    uint8_t*        d_out;      // last column, same stride
+    uint64_t        stride;     // elements between consecutive blocks in every per-byte array
+    const uint32_t* d_len;      // device copy of block lengths
+    const uint32_t* h_len;      // host copy (divisor tables are built on the host)
+    uint32_t        max_n, nblk;
+    uint32_t*       d_primary;
+    // workspace (u32 arrays are nblk*stride elements)
+    uint32_t *d_keyA, *d_keyB, *d_valA, *d_valB, *d_rankA, *d_rankB;
+    uint8_t*  d_flags;    // nblk*stride bytes
+    uint32_t* d_hist;     // radix_hist_bytes(max_n, nblk)
+    int*      d_tile_last;  // nblk * ceil(max_n/4096)
+    uint32_t *d_period, *d_ngroups, *d_notdone;
+    uint8_t*  d_done;
+    uint32_t *d_div_vals, *d_div_off, *d_div_cnt;
+    uint32_t  div_cap;
+    uint8_t*  d_bad;
+    uint32_t  bad_stride;
+    uint32_t* h_rounds;  // optional: number of doubling rounds executed
+};
+bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st);
+
+struct BwtInvArgs
+{
+    const uint8_t*  d_in;   // last column
+    uint8_t*        d_out;
+    uint64_t        stride;
+    const uint32_t* d_len;
+    const uint32_t* d_primary;
+    uint32_t        max_n, nblk;
+    uint32_t*       d_W;     // nblk*stride
+    uint32_t*       d_hist;
+    uint2*          d_walk;  // nblk * ibwt_kmax(max_n)
+    uint32_t*       d_woff;  // same
+    uint32_t*       d_orbit; // nblk
+};
+uint32_t ibwt_row_stride(uint32_t max_n);
+uint32_t ibwt_kmax(uint32_t max_n);
+bool     bwt_inverse_batch(const BwtInvArgs& a, cudaStream_t st);
+
+// ---- mtf.cu -------------------------------------------------------------------------------
+uint32_t mtf_segments(uint32_t max_n);
+bool     mtf_encode_batch(const uint8_t* d_in, uint8_t* d_out, uint64_t stride, const uint32_t* d_len, uint32_t max_n, uint32_t nblk,
+                          uint8_t* d_summ, uint16_t* d_scnt, uint8_t* d_state, cudaStream_t st);
+bool     mtf_decode_batch(const uint8_t* d_in, uint8_t* d_out, uint64_t stride, const uint32_t* d_len, uint32_t max_n, uint32_t nblk,
+                          uint8_t* d_summ, uint8_t* d_state, cudaStream_t st);
+
+// ---- rle.cu -------------------------------------------------------------------------------
+struct RleEncArgs
+{
+    const uint8_t*  d_in;
+    uint64_t        stride;
+    const uint32_t* d_len;
+    uint32_t        max_n, nblk;
+    uint8_t*        d_out;
+    uint64_t        out_stride;
+    uint32_t*       d_rlen;  // encoded size per block
+    uint32_t*       d_hist;  // 256 bins per block of the encoded bytes (input of the Huffman build)
+    int *d_t_first_head, *d_t_last_head, *d_t_first_nl, *d_t_last_nl;  // nblk * rle_enc_tiles(max_n) each
+    uint32_t* d_t_cnt;
+};
+bool     rle_encode_batch(const RleEncArgs& a, cudaStream_t st);
+uint32_t rle_enc_tiles(uint32_t max_n);
+
+struct RleDecArgs
+{
+    const uint8_t*  d_in;
+    uint64_t        stride;
+    const uint32_t* d_rlen;
+    uint32_t        max_r, nblk;
+    uint8_t*        d_out;
+    uint64_t        out_stride;
+    uint32_t        out_cap;   // blocks decoding to more than this many bytes fail
+    uint32_t*       d_nlen;    // decoded size per block, 0 on error
+    uint32_t*       d_err;     // per block, must be zeroed by the caller
+    uint8_t *       d_t_exit, *d_t_entry;  // nblk*tiles*rle_dec_entries(), nblk*tiles
+    uint32_t *      d_t_tok, *d_t_ocnt;    // nblk*tiles*32, nblk*tiles
+    bool            size_only;
+};
+bool     rle_decode_batch(const RleDecArgs& a, cudaStream_t st);
+uint32_t rle_dec_tiles(uint32_t max_r);
+uint32_t rle_dec_entries();
+
+// ---- huffman.cu ---------------------------------------------------------------------------
+struct HufEncArgs
+{
+    const uint8_t*  d_in;
+    uint64_t        stride;
+    const uint32_t* d_rlen;
+    uint32_t        max_r, nblk;
+    bool            compute_hist;  // false when the RLE emit kernel already filled d_hist
+    uint32_t*       d_hist;        // nblk*256
+    uint8_t*        d_hdr;         // nblk*268: lengths, orig_size, encoded_size are written here
+    uint32_t*       d_codes;       // nblk*256
+    uint32_t*       d_ok;          // nblk
+    uint32_t*       d_t_bits;      // nblk*huf_enc_tiles(max_r)
+    uint32_t*       d_clen;        // nblk
+    uint8_t*        d_out;
+    uint64_t        out_stride;
+};
+bool     huf_encode_batch(const HufEncArgs& a, cudaStream_t st);
+uint32_t huf_enc_tiles(uint32_t max_r);
+
+struct HufDecArgs
+{
+    const uint8_t*  d_pay;
+    uint64_t        pay_stride;
+    const uint32_t* d_clen;
+    const uint8_t*  d_hdr;  // nblk*268
+    uint32_t        max_c, nblk;
+    uint8_t*        d_out;
+    uint64_t        out_stride;  // must hold orig_size bytes per block
+    bra_huf_dec_t*  d_tabs;
+    uint32_t*       d_err;  // per block, zeroed by the caller
+    uint8_t *       d_sub_start, *d_sub_count;           // nblk*seqs*256
+    uint32_t *      d_seq_entry, *d_seq_exit, *d_seq_count;  // nblk*seqs
+    uint32_t *      d_end_bit, *d_changed;
+    uint32_t*       h_sweeps;
+};
+bool     huf_decode_batch(const HufDecArgs& a, cudaStream_t st);
+uint32_t huf_dec_seqs(uint32_t max_c);
+uint32_t huf_dec_subs_per_seq();
+
+}  // namespace bra

@@ -1,0 +1,564 @@
+// bwt.cu -- forward and inverse Burrows-Wheeler transform for a batch of blocks.
+//
+// FORWARD (replaces reference bra_bwt_encode2, src/encoders/bra_bwt.c:73-108)
+//   The reference sorts the n cyclic rotations with qsort_r and a byte-wise comparator and
+//   breaks ties between identical rotations by ascending start index (glibc's stable merge
+//   sort). Here the same order is built as a suffix array of the cyclic string:
+//     1. period detection: the smallest p | n with T[i] == T[(i+p) mod n]. Rotations i and i+p
+//        are identical, so it suffices to sort the p rotations of the primitive root (all
+//        distinct) and replicate each n/p times in ascending index -- exactly the tie rule.
+//     2. 4-byte keys + 4 LSD radix passes (sort.cu) order the rotations by their first 4 bytes.
+//     3. prefix doubling, Manber-Myers style: walking the current order j = 0..p-1, rotation
+//        SA[j]-h is appended to its own h-group, which a stable radix sort on rank[SA[j]-h]
+//        does in 2-3 passes; new group heads give the 2h-ranks. Repeats until every group is a
+//        singleton (all rotations of a primitive string differ, so this terminates with h < 2p).
+//     4. gather L[j] = T[SA[j/k] - 1], primary = k * (row of rotation 0), k = n/p.
+//
+// INVERSE (replaces reference bra_bwt_decode2, bra_bwt.c:133-168)
+//   transform[] is the stable sort of positions by byte value = one 8-bit radix pass, emitted
+//   as W[j] = transform[j] << 8 | F[j] so that the chase needs one load per output byte. The
+//   n-step dependent chase is cut into ~n/R independent walks that start at every R-th row
+//   (and at the primary row) and stop at the next start row; a per-block stitch orders the
+//   walks from the primary row and a second walk writes the bytes at their final offsets.
+#include "bra_common.cuh"
+#include "bra_kernels.h"
+
+#include <algorithm>
+#include <utility>
+#include <vector>
+
+namespace bra {
+
+#define EW_TILE 4096  // elementwise tile: 256 threads x 16 consecutive elements
+#define EW_THREADS 256
+
+// ------------------------------------------------------------------------------------------------
+// 1. period detection
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bwt_period_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len,
+                                                         const uint32_t* __restrict__ div_vals, const uint32_t* __restrict__ div_off,
+                                                         const uint32_t* __restrict__ div_cnt, uint8_t* __restrict__ bad, uint32_t bad_stride)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = len[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= n) return;
+    const uint8_t* T    = in + (uint64_t) b * stride;
+    const uint32_t tend = min(n, tile0 + EW_TILE);
+    const uint32_t cnt  = div_cnt[b];
+    const uint32_t* dv  = div_vals + div_off[b];
+    const uint32_t q    = min(n, 32u);
+    for (uint32_t di = 0; di < cnt; ++di)
+    {
+        const uint32_t d = dv[di];  // proper divisor of n
+        // cheap uniform pre-test on the first 32 bytes
+        const uint32_t l  = lane_id();
+        bool           ne = false;
+        if (l < q)
+        {
+            uint32_t j = l + d;
+            if (j >= n) j -= n;
+            ne = T[l] != T[j];
+        }
+        if (__any_sync(BRA_FULL, ne)) continue;  // same outcome in every warp of the CTA
+        bool mism = false;
+        for (uint32_t i = tile0 + threadIdx.x; i < tend; i += 256)
+        {
+            uint32_t j = i + d;
+            if (j >= n) j -= n;
+            mism |= T[i] != T[j];
+        }
+        if (__syncthreads_or(mism) && threadIdx.x == 0) bad[(uint64_t) b * bad_stride + di] = 1;
+    }
+}
+
+__global__ void bwt_period_select_kernel(const uint32_t* __restrict__ len, const uint32_t* __restrict__ div_vals,
+                                         const uint32_t* __restrict__ div_off, const uint32_t* __restrict__ div_cnt,
+                                         const uint8_t* __restrict__ bad, uint32_t bad_stride, uint32_t* __restrict__ period, uint32_t nblk)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    uint32_t p = len[b];
+    for (uint32_t di = 0; di < div_cnt[b]; ++di)
+        if (!bad[(uint64_t) b * bad_stride + di])
+        {
+            p = div_vals[div_off[b] + di];  // divisors are ascending: first survivor is the smallest period
+            break;
+        }
+    period[b] = p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. initial keys: first 4 bytes of every rotation of the primitive root, big endian
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t* __restrict__ in, uint64_t stride,
+                                                                   const uint32_t* __restrict__ period, uint32_t* __restrict__ keys,
+                                                                   uint32_t* __restrict__ vals)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t p = period[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= p) return;
+    const uint8_t* T    = in + (uint64_t) b * stride;
+    const uint64_t base = (uint64_t) b * stride;
+    const uint32_t tend = min(p, tile0 + EW_TILE);
+    for (uint32_t j = tile0 + threadIdx.x; j < tend; j += EW_THREADS)
+    {
+        uint32_t key = 0;
+        if (j + 3 < p)
+            key = ((uint32_t) T[j] << 24) | ((uint32_t) T[j + 1] << 16) | ((uint32_t) T[j + 2] << 8) | T[j + 3];
+        else
+        {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) key = (key << 8) | T[(j + d) % p];
+        }
+        keys[base + j] = key;
+        vals[base + j] = j;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 3. group heads and ranks
+// ------------------------------------------------------------------------------------------------
+// Pass A: head flag per sorted slot j (1 byte), last head of each tile, group count per block.
+//   MODE 0: head <=> sorted key differs from its left neighbour          (after the 4-byte sort)
+//   MODE 1: head <=> (rank[SA[j]], rank[SA[j]+h]) differs from the left   (doubling round)
+//           skeys[j] already equals rank[SA[j]] (it was the sort key).
+template <int MODE>
+__global__ void __launch_bounds__(EW_THREADS)
+    bwt_heads_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ sa, const uint32_t* __restrict__ rank, uint32_t h,
+                     uint64_t stride, const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, uint8_t* __restrict__ flags,
+                     int* __restrict__ tile_last, uint32_t tiles, uint32_t* __restrict__ ngroups)
+{
+    __shared__ int      s_last[8];
+    __shared__ uint32_t s_cnt[8];
+    const uint32_t      b = blockIdx.y;
+    if (skip[b]) return;
+    const uint32_t p     = period[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= p) return;
+    const uint64_t base = (uint64_t) b * stride;
+    const uint32_t j0   = tile0 + threadIdx.x * 16;
+    const uint32_t hm   = h % p;
+
+    int      last = -1;
+    uint32_t cnt  = 0;
+    if (j0 < p)
+    {
+        const uint32_t m = min(16u, p - j0);
+        uint32_t       prevk = 0, prevg = 0;
+        if (j0 > 0)
+        {
+            prevk = skeys[base + j0 - 1];
+            if (MODE == 1)
+            {
+                uint32_t x = sa[base + j0 - 1] + hm;
+                if (x >= p) x -= p;
+                prevg = rank[base + x];
+            }
+        }
+        uint32_t fl[4] = {0, 0, 0, 0};
+        for (uint32_t i = 0; i < m; ++i)
+        {
+            const uint32_t j = j0 + i;
+            const uint32_t k = skeys[base + j];
+            uint32_t       g = 0;
+            if (MODE == 1)
+            {
+                uint32_t x = sa[base + j] + hm;
+                if (x >= p) x -= p;
+                g = rank[base + x];
+            }
+            const bool head = (j == 0) || k != prevk || (MODE == 1 && g != prevg);
+            if (head)
+            {
+                fl[i >> 2] |= 1u << ((i & 3) * 8);
+                last = (int) j;
+                ++cnt;
+            }
+            prevk = k;
+            prevg = g;
+        }
+        if (m == 16)
+            *reinterpret_cast<uint4*>(flags + base + j0) = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+        else
+            for (uint32_t i = 0; i < m; ++i) flags[base + j0 + i] = (fl[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        last = max(last, __shfl_xor_sync(BRA_FULL, last, d));
+        cnt += __shfl_xor_sync(BRA_FULL, cnt, d);
+    }
+    if (lane_id() == 0)
+    {
+        s_last[warp_id()] = last;
+        s_cnt[warp_id()]  = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        int      L = -1;
+        uint32_t c = 0;
+        for (int i = 0; i < 8; ++i)
+        {
+            L = max(L, s_last[i]);
+            c += s_cnt[i];
+        }
+        tile_last[(uint64_t) b * tiles + blockIdx.x] = L;
+        atomicAdd(&ngroups[b], c);
+    }
+}
+
+// Pass B: rank_out[SA[j]] = index of the head of j's group.
+__global__ void __launch_bounds__(EW_THREADS)
+    bwt_ranks_kernel(const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags, uint64_t stride, const uint32_t* __restrict__ period,
+                     const uint8_t* __restrict__ skip, const int* __restrict__ tile_last, uint32_t tiles, uint32_t* __restrict__ rank_out)
+{
+    __shared__ int red[33];
+    const uint32_t b = blockIdx.y;
+    if (skip[b]) return;
+    const uint32_t p     = period[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= p) return;
+    const uint64_t base = (uint64_t) b * stride;
+
+    // carry-in: last head before this tile
+    int carry = 0;
+    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += EW_THREADS) carry = max(carry, tile_last[(uint64_t) b * tiles + t]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) carry = max(carry, __shfl_xor_sync(BRA_FULL, carry, d));
+    if (lane_id() == 0) red[warp_id()] = carry;
+    __syncthreads();
+    carry = red[0];
+    for (int i = 1; i < 8; ++i) carry = max(carry, red[i]);
+    __syncthreads();
+
+    const uint32_t j0 = tile0 + threadIdx.x * 16;
+    const uint32_t m  = j0 < p ? min(16u, p - j0) : 0u;
+    uint8_t        f[16];
+    int            mylast = -1;
+    for (uint32_t i = 0; i < m; ++i)
+    {
+        f[i] = flags[base + j0 + i];
+        if (f[i]) mylast = (int) (j0 + i);
+    }
+    int run = max(block_excl_max(mylast, -1, red), carry);
+    for (uint32_t i = 0; i < m; ++i)
+    {
+        if (f[i]) run = (int) (j0 + i);
+        rank_out[base + sa[base + j0 + i]] = (uint32_t) run;
+    }
+}
+
+// Block state machine kept in done[b]: 0 = still sorting, 1 = order complete this round (its last
+// column is gathered right away from the buffer that currently holds its suffix array, because
+// finished blocks are skipped by later rounds and the ping-pong buffers move on), 2 = finished.
+// *notdone counts the blocks still sorting.
+__global__ void bwt_check_done_kernel(const uint32_t* __restrict__ period, uint32_t* __restrict__ ngroups, uint8_t* __restrict__ done,
+                                      uint32_t* __restrict__ notdone, uint32_t nblk)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const uint8_t d = done[b];
+    if (d == 1)
+        done[b] = 2;
+    else if (d == 0)
+    {
+        if (ngroups[b] >= period[b])
+            done[b] = 1;
+        else
+            atomicAdd(notdone, 1u);
+    }
+    ngroups[b] = 0;
+}
+
+// doubling round, step 1: keys/vals in current-order traversal
+__global__ void __launch_bounds__(EW_THREADS)
+    bwt_dbl_prepare_kernel(const uint32_t* __restrict__ sa, const uint32_t* __restrict__ rank, uint32_t h, uint64_t stride,
+                           const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, uint32_t* __restrict__ keys,
+                           uint32_t* __restrict__ vals)
+{
+    const uint32_t b = blockIdx.y;
+    if (skip[b]) return;
+    const uint32_t p     = period[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= p) return;
+    const uint64_t base = (uint64_t) b * stride;
+    const uint32_t tend = min(p, tile0 + EW_TILE);
+    const uint32_t hm   = h % p;
+    for (uint32_t j = tile0 + threadIdx.x; j < tend; j += EW_THREADS)
+    {
+        const uint32_t s = sa[base + j];
+        const uint32_t v = s >= hm ? s - hm : s + p - hm;
+        vals[base + j]   = v;
+        keys[base + j]   = rank[base + v];
+    }
+}
+
+// 4. last column + primary index
+__global__ void __launch_bounds__(EW_THREADS)
+    bwt_gather_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ sa, uint64_t stride, const uint32_t* __restrict__ len,
+                      const uint32_t* __restrict__ period, const uint8_t* __restrict__ done, uint8_t* __restrict__ out,
+                      uint32_t* __restrict__ primary)
+{
+    const uint32_t b = blockIdx.y;
+    if (done[b] != 1) return;
+    const uint32_t n = len[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= n) return;
+    const uint32_t p    = period[b];
+    const uint32_t k    = n / p;
+    const uint64_t base = (uint64_t) b * stride;
+    const uint8_t* T    = in + base;
+    const uint32_t tend = min(n, tile0 + EW_TILE);
+    for (uint32_t j = tile0 + threadIdx.x; j < tend; j += EW_THREADS)
+    {
+        const uint32_t q = (k == 1) ? j : j / k;
+        const uint32_t s = sa[base + q];
+        out[base + j]    = T[s == 0 ? p - 1 : s - 1];
+        if (s == 0 && q * k == j) primary[b] = j;  // identical rotations are in ascending index: rotation 0 is the first
+    }
+}
+
+static void host_divisors(uint32_t n, std::vector<uint32_t>& out)
+{
+    std::vector<uint32_t> hi;
+    for (uint32_t d = 1; (uint64_t) d * d <= n; ++d)
+        if (n % d == 0)
+        {
+            if (d < n) out.push_back(d);
+            const uint32_t e = n / d;
+            if (e != d && e < n) hi.push_back(e);
+        }
+    for (size_t i = hi.size(); i-- > 0;) out.push_back(hi[i]);
+}
+
+bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
+{
+    const uint32_t nblk = a.nblk, max_n = a.max_n;
+    if (nblk == 0) return true;
+    const uint32_t tiles = bra_div_up(max_n, EW_TILE);
+    const dim3     grid(tiles, nblk);
+
+    // ---- period detection (divisor tables built on the host from the known block lengths)
+    {
+        std::vector<uint32_t> vals, off(nblk), cnt(nblk);
+        std::vector<std::pair<uint32_t, std::pair<uint32_t, uint32_t>>> seen;  // n -> (off, cnt)
+        uint32_t maxcnt = 1;
+        for (uint32_t b = 0; b < nblk; ++b)
+        {
+            const uint32_t n = a.h_len[b];
+            bool           found = false;
+            for (auto& s : seen)
+                if (s.first == n)
+                {
+                    off[b] = s.second.first;
+                    cnt[b] = s.second.second;
+                    found  = true;
+                    break;
+                }
+            if (!found)
+            {
+                const uint32_t o = (uint32_t) vals.size();
+                host_divisors(n, vals);
+                off[b] = o;
+                cnt[b] = (uint32_t) vals.size() - o;
+                seen.push_back({n, {o, cnt[b]}});
+            }
+            maxcnt = std::max(maxcnt, cnt[b]);
+        }
+        if (vals.empty()) vals.push_back(1);
+        if (vals.size() > a.div_cap || maxcnt > a.bad_stride)
+        {
+            bra_b200_log_error("bwt: divisor table overflow (%zu values, %u per block)", vals.size(), maxcnt);
+            return false;
+        }
+        BRA_CUDA_TRY(cudaMemcpyAsync(a.d_div_vals, vals.data(), vals.size() * 4, cudaMemcpyHostToDevice, st));
+        BRA_CUDA_TRY(cudaMemcpyAsync(a.d_div_off, off.data(), nblk * 4, cudaMemcpyHostToDevice, st));
+        BRA_CUDA_TRY(cudaMemcpyAsync(a.d_div_cnt, cnt.data(), nblk * 4, cudaMemcpyHostToDevice, st));
+        BRA_CUDA_TRY(cudaMemsetAsync(a.d_bad, 0, (size_t) nblk * a.bad_stride, st));
+        // the pageable-host staging vectors die at scope exit: the copies above must have landed
+        BRA_CUDA_TRY(cudaStreamSynchronize(st));
+        BRA_LAUNCH(P_BWT_PERIOD, st, bwt_period_kernel<<<grid, 256, 0, st>>>(a.d_in, a.stride, a.d_len, a.d_div_vals, a.d_div_off, a.d_div_cnt, a.d_bad, a.bad_stride));
+        BRA_LAUNCH(P_BWT_PERIOD, st, bwt_period_select_kernel<<<bra_div_up(nblk, 128), 128, 0, st>>>(a.d_len, a.d_div_vals, a.d_div_off, a.d_div_cnt, a.d_bad,
+                                                                       a.bad_stride, a.d_period, nblk));
+    }
+
+    BRA_CUDA_TRY(cudaMemsetAsync(a.d_done, 0, nblk, st));
+    BRA_CUDA_TRY(cudaMemsetAsync(a.d_ngroups, 0, nblk * 4, st));
+
+    // ---- 4-byte radix sort
+    uint32_t *kA = a.d_keyA, *kB = a.d_keyB, *vA = a.d_valA, *vB = a.d_valB;
+    BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, kA, vA));
+    for (uint32_t shift = 0; shift < 32; shift += 8)
+    {
+        if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, shift, a.d_hist, st)) return false;
+        std::swap(kA, kB);
+        std::swap(vA, vB);
+    }
+    uint32_t *rk = a.d_rankA, *rk2 = a.d_rankB;
+    BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<0><<<grid, EW_THREADS, 0, st>>>(kA, vA, nullptr, 0, a.stride, a.d_period, a.d_done, a.d_flags, a.d_tile_last, tiles,
+                                                      a.d_ngroups));
+    BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, a.d_flags, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk));
+
+    uint32_t h = 4, rounds = 0;
+    uint32_t key_bits = 1;
+    while ((1ull << key_bits) < max_n) ++key_bits;
+    for (;;)
+    {
+        BRA_CUDA_TRY(cudaMemsetAsync(a.d_notdone, 0, 4, st));
+        BRA_LAUNCH(P_BWT_MISC, st, bwt_check_done_kernel<<<bra_div_up(nblk, 128), 128, 0, st>>>(a.d_period, a.d_ngroups, a.d_done, a.d_notdone, nblk));
+        BRA_LAUNCH(P_BWT_GATHER, st, bwt_gather_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, vA, a.stride, a.d_len, a.d_period, a.d_done, a.d_out, a.d_primary));
+        uint32_t notdone = 0;
+        BRA_CUDA_TRY(cudaMemcpyAsync(&notdone, a.d_notdone, 4, cudaMemcpyDeviceToHost, st));
+        BRA_CUDA_TRY(cudaStreamSynchronize(st));
+        if (notdone == 0) break;
+        if (h >= 2u * max_n + 8u)
+        {
+            bra_b200_log_error("bwt: prefix doubling did not converge (h=%u, max_n=%u, %u blocks left)", h, max_n, notdone);
+            return false;
+        }
+        BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, h, a.stride, a.d_period, a.d_done, kB, vB));
+        std::swap(kA, kB);
+        std::swap(vA, vB);
+        for (uint32_t shift = 0; shift < key_bits; shift += 8)
+        {
+            if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, shift, a.d_hist, st)) return false;
+            std::swap(kA, kB);
+            std::swap(vA, vB);
+        }
+        BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(kA, vA, rk, h, a.stride, a.d_period, a.d_done, a.d_flags, a.d_tile_last, tiles,
+                                                          a.d_ngroups));
+        BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, a.d_flags, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk2));
+        std::swap(rk, rk2);
+        h *= 2;
+        ++rounds;
+    }
+    if (a.h_rounds) *a.h_rounds = rounds;
+    BRA_CUDA_TRY(cudaGetLastError());
+    return true;
+}
+
+// ================================================================================================
+// INVERSE
+// ================================================================================================
+#define IB_THREADS 128
+#define IB_INVALID 0xFFFFFFFFu
+
+__device__ __forceinline__ uint32_t ib_rows(uint32_t n, uint32_t R) { return (n + R - 1) / R; }
+
+// Walk 1: from every start row (multiples of R, plus the primary row as walker K) follow
+// W[idx] >> 8 until the next start row; record the walk length and which walker it runs into.
+__global__ void __launch_bounds__(IB_THREADS)
+    ibwt_walk_len_kernel(const uint32_t* __restrict__ W, uint64_t stride, const uint32_t* __restrict__ len, const uint32_t* __restrict__ primary,
+                         uint32_t R, uint32_t kmax, uint2* __restrict__ walk /* (len, succ) */, uint32_t* __restrict__ woff)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = len[b];
+    if (n == 0) return;
+    const uint32_t K  = ib_rows(n, R);
+    const uint32_t w  = blockIdx.x * IB_THREADS + threadIdx.x;
+    if (w > K) return;
+    const uint32_t pi = primary[b];
+    const uint32_t* Wb = W + (uint64_t) b * stride;
+    uint32_t idx = (w == K) ? pi : w * R;
+    uint32_t steps = 0;
+    do
+    {
+        idx = Wb[idx] >> 8;
+        ++steps;
+    } while (idx != pi && (idx % R) != 0);
+    const uint32_t succ = (idx == pi) ? K : idx / R;
+    walk[(uint64_t) b * kmax + w] = make_uint2(steps, succ);
+    woff[(uint64_t) b * kmax + w] = IB_INVALID;
+}
+
+// Stitch: order the walks from the primary row. If the chain closes before n bytes are covered the
+// text is a repetition of that orbit (periodic input): orbit[b] < n and every walk is replicated.
+__global__ void ibwt_stitch_kernel(const uint32_t* __restrict__ len, uint32_t R, uint32_t kmax, const uint2* __restrict__ walk,
+                                   uint32_t* __restrict__ woff, uint32_t* __restrict__ orbit, uint32_t nblk)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const uint32_t n = len[b];
+    if (n == 0)
+    {
+        orbit[b] = 0;
+        return;
+    }
+    const uint32_t K   = ib_rows(n, R);
+    const uint2*   wk  = walk + (uint64_t) b * kmax;
+    uint32_t*      off = woff + (uint64_t) b * kmax;
+    uint32_t w = K, o = 0;
+    while (o < n && off[w] == IB_INVALID)
+    {
+        const uint2 e = wk[w];
+        off[w]        = o;
+        o += e.x;
+        w = e.y;
+    }
+    orbit[b] = o;  // == n unless the chain closed early
+}
+
+// Walk 2: emit F[idx] = W[idx] & 0xFF at the stitched offsets (replicated every `orbit` bytes).
+__global__ void __launch_bounds__(IB_THREADS)
+    ibwt_walk_emit_kernel(const uint32_t* __restrict__ W, uint64_t stride, const uint32_t* __restrict__ len, const uint32_t* __restrict__ primary,
+                          uint32_t R, uint32_t kmax, const uint2* __restrict__ walk, const uint32_t* __restrict__ woff,
+                          const uint32_t* __restrict__ orbit, uint8_t* __restrict__ out)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = len[b];
+    if (n == 0) return;
+    const uint32_t K = ib_rows(n, R);
+    const uint32_t w = blockIdx.x * IB_THREADS + threadIdx.x;
+    if (w > K) return;
+    const uint32_t o0 = woff[(uint64_t) b * kmax + w];
+    if (o0 == IB_INVALID) return;  // not on the primary row's orbit
+    const uint32_t steps = walk[(uint64_t) b * kmax + w].x;
+    const uint32_t q     = orbit[b];
+    const uint32_t* Wb   = W + (uint64_t) b * stride;
+    uint8_t*        ob   = out + (uint64_t) b * stride;
+    uint32_t idx = (w == K) ? primary[b] : w * R;
+    if (q >= n)
+    {
+        for (uint32_t t = 0; t < steps; ++t)
+        {
+            const uint32_t e = Wb[idx];
+            if (o0 + t < n) ob[o0 + t] = (uint8_t) e;
+            idx = e >> 8;
+        }
+    }
+    else
+    {
+        for (uint32_t t = 0; t < steps; ++t)
+        {
+            const uint32_t e = Wb[idx];
+            for (uint32_t pos = o0 + t; pos < n; pos += q) ob[pos] = (uint8_t) e;
+            idx = e >> 8;
+        }
+    }
+}
+
+uint32_t ibwt_row_stride(uint32_t max_n)
+{
+    uint32_t R = 128;
+    while ((uint64_t) R * 8192 < max_n) R *= 2;
+    return R;
+}
+uint32_t ibwt_kmax(uint32_t max_n) { return (max_n + ibwt_row_stride(max_n) - 1) / ibwt_row_stride(max_n) + 1; }
+
+bool bwt_inverse_batch(const BwtInvArgs& a, cudaStream_t st)
+{
+    if (a.nblk == 0 || a.max_n == 0) return true;
+    const uint32_t R = ibwt_row_stride(a.max_n), kmax = ibwt_kmax(a.max_n);
+    if (!radix_pass_u8_index_packed(a.d_in, a.d_W, a.stride, a.d_len, a.max_n, a.nblk, a.d_hist, st)) return false;
+    const dim3 grid(bra_div_up(kmax, IB_THREADS), a.nblk);
+    BRA_LAUNCH(P_IBWT_WALK_LEN, st, ibwt_walk_len_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff));
+    BRA_LAUNCH(P_IBWT_STITCH, st, ibwt_stitch_kernel<<<bra_div_up(a.nblk, 32), 32, 0, st>>>(a.d_len, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.nblk));
+    BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_walk_emit_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_out));
+    BRA_CUDA_TRY(cudaGetLastError());
+    return true;
+}
+
+}  // namespace bra

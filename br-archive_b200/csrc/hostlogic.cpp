@@ -1,0 +1,64 @@
+// hostlogic.cpp -- host-only build of the scalar logic the kernels share with the host (bra_hd.h),
+// exported for the CPU test-suite (tests/test_host_logic.py). Not part of the product library.
+#include "bra_hd.h"
+
+#include <stdlib.h>
+#include <string.h>
+
+extern "C" {
+
+uint32_t hl_gf_mul(uint32_t a, uint32_t b) { return bra_gf_mul(a, b); }
+
+uint32_t hl_crc_combine(uint32_t a, uint32_t b, uint64_t len_b)
+{
+    bra_gf_pow_t t;
+    bra_gf_init_pow(&t);
+    return bra_crc_combine(&t, a, b, len_b);
+}
+
+uint32_t hl_huf_lengths(const uint32_t* freq, uint8_t* lengths)
+{
+    bra_huf_build_ws_t* ws = (bra_huf_build_ws_t*) malloc(sizeof(bra_huf_build_ws_t));
+    const uint32_t      k  = bra_huf_build_lengths(freq, lengths, ws);
+    free(ws);
+    return k;
+}
+
+void hl_huf_canonical(const uint8_t* lengths, uint32_t* codes) { bra_huf_canonical(lengths, codes); }
+
+// sequential decode through the device decode tables: returns 0 ok, -1 tables rejected, -2 invalid code, -3 out of data
+int hl_huf_decode(const uint8_t* lengths, const uint8_t* data, uint32_t nbytes, uint32_t nsym, uint8_t* out)
+{
+    bra_huf_dec_t d;
+    if (!bra_huf_make_dec(lengths, &d)) return -1;
+    uint64_t pos = 0;
+    const uint64_t end = (uint64_t) nbytes * 8;
+    for (uint32_t i = 0; i < nsym; ++i)
+    {
+        uint32_t w = 0;
+        for (int k = 0; k < 5; ++k)
+        {
+            const uint64_t byte = (pos >> 3) + k;
+            const uint64_t v    = byte < nbytes ? data[byte] : 0;
+            // assemble 40 bits then take 32 from the bit offset
+            if (k == 0) w = 0;
+            (void) v;
+        }
+        uint64_t acc = 0;
+        for (int k = 0; k < 5; ++k)
+        {
+            const uint64_t byte = (pos >> 3) + k;
+            acc = (acc << 8) | (byte < nbytes ? data[byte] : 0);
+        }
+        w = (uint32_t) ((acc >> (8 - (pos & 7))) & 0xFFFFFFFFull);
+        uint8_t        sym;
+        const uint32_t l = bra_huf_decode_one(&d, w, &sym);
+        if (l == 0) return -2;
+        if (pos + l > end) return -3;
+        out[i] = sym;
+        pos += l;
+    }
+    return 0;
+}
+
+}  // extern "C"

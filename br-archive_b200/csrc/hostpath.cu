@@ -1,0 +1,329 @@
+// hostpath.cu -- host-buffer entry points: what bra_io_file_chunks_compress_file /
+// decompress_file need (reference src/io/lib_bra_io_file_chunks.c:169-441), minus the FILE I/O.
+//
+// encode: host bytes -> H2D -> batched chain -> device-side gather into the on-disk chunk stream
+//         (3-byte index + 264-byte Huffman header + payload per chunk, chunks.c:81-92,252-256)
+//         -> one D2H copy per batch. The per-entry CRC chain of chunks.c:248-249 is folded on the
+//         host from the per-chunk CRCs the GPU produced (two GF(2) multiplications per chunk).
+// decode: the stream is walked on the host only to find chunk boundaries (each header names its
+//         payload size), uploaded as is, scattered on the device into the batched layout, decoded,
+//         and the plain bytes come back with one D2H copy per batch.
+#include "bra_common.cuh"
+#include "bra_kernels.h"
+#include "pipeline.h"
+
+#include <algorithm>
+#include <string.h>
+#include <vector>
+
+using namespace bra;
+
+namespace {
+
+// out offsets (exclusive scan of 267 + clen) for up to 32768 blocks: one CTA
+__global__ void __launch_bounds__(1024) stream_offsets_kernel(const uint8_t* __restrict__ hdr, uint32_t nblk, uint64_t* __restrict__ off)
+{
+    __shared__ uint32_t red[34];
+    uint64_t            carry = 0;
+    for (uint32_t base = 0; base < nblk; base += 1024)
+    {
+        const uint32_t b = base + threadIdx.x;
+        uint32_t       v = 0;
+        if (b < nblk)
+        {
+            const uint8_t* h = hdr + (uint64_t) b * 268 + 264;
+            v = 267u + ((uint32_t) h[0] | ((uint32_t) h[1] << 8) | ((uint32_t) h[2] << 16) | ((uint32_t) h[3] << 24));
+        }
+        uint32_t       tot;
+        const uint32_t ex = block_excl_add(v, red, &tot);
+        if (b < nblk) off[b] = carry + ex;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) off[nblk] = carry;
+}
+
+// gather: out[off[b] ..) = hdr268[b][0..3) | hdr268[b][4..268) | payload[b][0..clen)
+__global__ void __launch_bounds__(256)
+    stream_gather_kernel(const uint8_t* __restrict__ hdr, const uint8_t* __restrict__ pay, uint64_t pay_stride, const uint64_t* __restrict__ off,
+                         uint8_t* __restrict__ out)
+{
+    const uint32_t b    = blockIdx.y;
+    const uint64_t o    = off[b];
+    const uint32_t size = (uint32_t) (off[b + 1] - o);  // 267 + clen
+    const uint8_t* h    = hdr + (uint64_t) b * 268;
+    const uint8_t* p    = pay + (uint64_t) b * pay_stride;
+    for (uint32_t i = blockIdx.x * 256 * 16 + threadIdx.x; i < min(size, (blockIdx.x + 1) * 256u * 16u); i += 256)
+        out[o + i] = i < 3 ? h[i] : (i < 267 ? h[i + 1] : p[i - 267]);
+}
+
+// scatter: inverse of the gather, plus zero slack after each payload
+__global__ void __launch_bounds__(256)
+    stream_scatter_kernel(const uint8_t* __restrict__ in, const uint64_t* __restrict__ off, uint8_t* __restrict__ hdr, uint8_t* __restrict__ pay,
+                          uint64_t pay_stride)
+{
+    const uint32_t b    = blockIdx.y;
+    const uint64_t o    = off[b];
+    const uint32_t size = (uint32_t) (off[b + 1] - o);
+    uint8_t*       h    = hdr + (uint64_t) b * 268;
+    uint8_t*       p    = pay + (uint64_t) b * pay_stride;
+    for (uint32_t i = blockIdx.x * 256 * 16 + threadIdx.x; i < min(size, (blockIdx.x + 1) * 256u * 16u); i += 256)
+    {
+        const uint8_t v = in[o + i];
+        if (i < 3)
+            h[i] = v;
+        else if (i < 267)
+            h[i + 1] = v;
+        else
+            p[i - 267] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) h[3] = 0;  // index is 3 bytes on disk, 4 in memory (chunks.c:52-64)
+}
+
+__global__ void compact_out_kernel(const uint8_t* __restrict__ src, uint32_t block, const uint32_t* __restrict__ len, const uint64_t* __restrict__ off,
+                                   uint8_t* __restrict__ dst)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = len[b];
+    const uint64_t o = off[b];
+    for (uint32_t i = blockIdx.x * 256 * 16 + threadIdx.x; i < min(n, (blockIdx.x + 1) * 256u * 16u); i += 256)
+        dst[o + i] = src[(uint64_t) b * block + i];
+}
+
+}  // namespace
+
+extern "C" uint64_t bra_b200_encode_bound(const bra_b200_ctx_t* c, uint64_t total)
+{
+    if (!c) return 0;
+    const uint64_t nblk = (total + bra_b200_block_size(c) - 1) / bra_b200_block_size(c);
+    return nblk * (267 + bra_b200_payload_stride(c));
+}
+
+extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64_t total, uint8_t* out, uint64_t out_cap, uint64_t* out_size,
+                                    uint32_t* crc_chain)
+{
+    if (!c || !in || !out || !out_size || total == 0)
+    {
+        bra_b200_log_error("bra_b200_encode_host: invalid arguments");
+        return 1;
+    }
+    if (cudaSetDevice(ctx_device(c)) != cudaSuccess) return 2;
+    const uint32_t S  = bra_b200_block_size(c);
+    const uint32_t MB = bra_b200_max_batch(c);
+    const uint64_t PS = bra_b200_payload_stride(c);
+    const uint64_t nblk_total = (total + S - 1) / S;
+    cudaStream_t   st = ctx_stream(c);
+    *out_size         = 0;
+
+    // device staging: input | hdr | payload | stream | offsets | crcs
+    const uint64_t in_b = (uint64_t) MB * S, hdr_b = (uint64_t) MB * 268 + 256, pay_b = (uint64_t) MB * PS, str_b = (uint64_t) MB * (267 + PS),
+                   off_b = ((uint64_t) MB + 1) * 8 + 256, crc_b = (uint64_t) MB * 8 + 256;
+    uint8_t* io = ctx_io_buffer(c, in_b + hdr_b + pay_b + str_b + off_b + crc_b + 4096);
+    if (!io) return 3;
+    uint8_t*  d_in  = io;
+    uint8_t*  d_hdr = d_in + in_b;
+    uint8_t*  d_pay = d_hdr + hdr_b;
+    uint8_t*  d_str = d_pay + pay_b;
+    uint64_t* d_off = reinterpret_cast<uint64_t*>(d_str + ((str_b + 255) / 256) * 256);
+    uint32_t* d_crc = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_off) + off_b);
+    uint32_t* d_hcrc = d_crc + MB;
+
+    const bra_gf_pow_t*   pw = crc_host_pow();
+    std::vector<uint32_t> h_crc(2 * (size_t) MB);
+    uint32_t              crc = crc_chain ? *crc_chain : 0;
+    uint64_t              produced = 0;
+    for (uint64_t b0 = 0; b0 < nblk_total; b0 += MB)
+    {
+        const uint32_t nb    = (uint32_t) std::min<uint64_t>(MB, nblk_total - b0);
+        const uint64_t bytes = std::min<uint64_t>((uint64_t) nb * S, total - b0 * S);
+        const uint32_t last  = (uint32_t) (bytes - (uint64_t) (nb - 1) * S);
+        if (cudaMemcpyAsync(d_in, in + b0 * S, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return 4;
+        if (!encode_batch(c, d_in, nb, last, d_hdr, d_pay, d_crc, st)) return 5;
+        if (!crc_headers(d_hdr, 268, nb, d_hcrc, st)) return 5;
+        BRA_LAUNCH(P_GLUE, st, stream_offsets_kernel<<<1, 1024, 0, st>>>(d_hdr, nb, d_off));
+        const uint32_t gx = bra_div_up(267 + PS, 4096);
+        BRA_LAUNCH(P_GLUE, st, stream_gather_kernel<<<dim3(gx, nb), 256, 0, st>>>(d_hdr, d_pay, PS, d_off, d_str));
+        uint64_t str_size = 0;
+        if (cudaMemcpyAsync(&str_size, d_off + nb, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+        if (cudaMemcpyAsync(h_crc.data(), d_crc, (size_t) nb * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+        if (cudaMemcpyAsync(h_crc.data() + MB, d_hcrc, (size_t) nb * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
+        if (produced + str_size > out_cap)
+        {
+            bra_b200_log_error("bra_b200_encode_host: output buffer too small");
+            return 6;
+        }
+        if (cudaMemcpyAsync(out + produced, d_str, str_size, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+        // CRC chain of reference chunks.c:248-249 while the copy runs
+        for (uint32_t b = 0; b < nb; ++b)
+        {
+            const uint32_t n = (b + 1 == nb) ? last : S;
+            crc = bra_crc_combine(pw, crc, h_crc[MB + b], 268);
+            crc = bra_crc_combine(pw, crc, h_crc[b], n);
+        }
+        if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
+        produced += str_size;
+    }
+    *out_size = produced;
+    if (crc_chain) *crc_chain = crc;
+    return 0;
+}
+
+extern "C" int bra_b200_decode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap, uint64_t* out_size,
+                                    uint32_t* crc_chain)
+{
+    if (!c || !in || !out || !out_size)
+    {
+        bra_b200_log_error("bra_b200_decode_host: invalid arguments");
+        return 1;
+    }
+    if (cudaSetDevice(ctx_device(c)) != cudaSuccess) return 2;
+    const uint32_t S  = bra_b200_block_size(c);
+    const uint32_t MB = bra_b200_max_batch(c);
+    const uint64_t PS = bra_b200_payload_stride(c);
+    cudaStream_t   st = ctx_stream(c);
+    *out_size         = 0;
+
+    const uint64_t str_b = (uint64_t) MB * (267 + PS), hdr_b = (uint64_t) MB * 268 + 256, pay_b = (uint64_t) MB * PS, out_b = (uint64_t) MB * S,
+                   off_b = ((uint64_t) MB + 1) * 8 + 256, misc_b = (uint64_t) MB * 16 + 256;
+    uint8_t* io = ctx_io_buffer(c, str_b + hdr_b + pay_b + 2 * out_b + 2 * off_b + misc_b + 8192);
+    if (!io) return 3;
+    uint8_t*  d_str  = io;
+    uint8_t*  d_hdr  = d_str + ((str_b + 255) / 256) * 256;
+    uint8_t*  d_pay  = d_hdr + hdr_b;
+    uint8_t*  d_out  = d_pay + pay_b;
+    uint8_t*  d_cmp  = d_out + out_b;
+    uint64_t* d_off  = reinterpret_cast<uint64_t*>(d_cmp + out_b);
+    uint64_t* d_ooff = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(d_off) + off_b);
+    uint32_t* d_len  = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_ooff) + off_b);
+    uint32_t* d_crc  = d_len + MB;
+    uint32_t* d_stat = d_crc + MB;
+    uint32_t* d_hcrc = d_stat + MB;
+
+    const bra_gf_pow_t*   pw = crc_host_pow();
+    std::vector<uint64_t> h_off(MB + 1), h_ooff(MB + 1);
+    std::vector<uint32_t> h_misc(4 * (size_t) MB);
+    uint32_t              crc = crc_chain ? *crc_chain : 0;
+    uint64_t              pos = 0, produced = 0;
+    while (pos < in_size)
+    {
+        // find the chunk boundaries of the next batch (reference chunks.c:338-357, :414)
+        uint32_t nb = 0, max_r = 0, max_c = 0;
+        uint64_t p  = pos;
+        while (nb < MB && p < in_size)
+        {
+            if (in_size - p < 267)
+            {
+                bra_b200_log_error("bra_b200_decode_host: truncated chunk header at offset %llu", (unsigned long long) p);
+                return 7;
+            }
+            const uint8_t* h = in + p + 3 + 256;
+            const uint32_t r = (uint32_t) h[0] | ((uint32_t) h[1] << 8) | ((uint32_t) h[2] << 16) | ((uint32_t) h[3] << 24);
+            const uint32_t cc = (uint32_t) h[4] | ((uint32_t) h[5] << 8) | ((uint32_t) h[6] << 16) | ((uint32_t) h[7] << 24);
+            if (cc == 0 || r == 0 || cc > PS - 32 || in_size - p - 267 < cc)
+            {
+                bra_b200_log_error("bra_b200_decode_host: chunk header not valid at offset %llu", (unsigned long long) p);
+                return 7;
+            }
+            h_off[nb] = p - pos;
+            max_r     = std::max(max_r, r);
+            max_c     = std::max(max_c, cc);
+            p += 267 + cc;
+            ++nb;
+        }
+        h_off[nb] = p - pos;
+        if (cudaMemcpyAsync(d_str, in + pos, p - pos, cudaMemcpyHostToDevice, st) != cudaSuccess) return 4;
+        if (cudaMemcpyAsync(d_off, h_off.data(), ((size_t) nb + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) return 4;
+        const uint32_t gx = bra_div_up(267 + (uint64_t) max_c, 4096);
+        BRA_LAUNCH(P_GLUE, st, stream_scatter_kernel<<<dim3(gx, nb), 256, 0, st>>>(d_str, d_off, d_hdr, d_pay, PS));
+        if (!decode_batch(c, d_hdr, d_pay, nb, max_r, max_c, d_out, d_len, d_crc, d_stat, st)) return 5;
+        if (!crc_headers(d_hdr, 268, nb, d_hcrc, st)) return 5;
+        if (cudaMemcpyAsync(h_misc.data(), d_len, (size_t) 4 * MB * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
+        uint64_t o = 0;
+        for (uint32_t b = 0; b < nb; ++b)
+        {
+            if (h_misc[2 * (size_t) MB + b] != 0)
+            {
+                bra_b200_log_error("bra_b200_decode_host: chunk %u of the batch at offset %llu is corrupt", b, (unsigned long long) pos);
+                return 8;
+            }
+            h_ooff[b] = o;
+            o += h_misc[b];
+            crc = bra_crc_combine(pw, crc, h_misc[3 * (size_t) MB + b], 268);  // chunks.c:396
+            crc = bra_crc_combine(pw, crc, h_misc[(size_t) MB + b], h_misc[b]); // chunks.c:397
+        }
+        h_ooff[nb] = o;
+        if (produced + o > out_cap)
+        {
+            bra_b200_log_error("bra_b200_decode_host: output buffer too small");
+            return 6;
+        }
+        // full blocks are already contiguous; compact only when some block is short
+        const uint8_t* src = d_out;
+        bool           contiguous = true;
+        for (uint32_t b = 0; b + 1 < nb; ++b) contiguous &= h_misc[b] == S;
+        if (!contiguous)
+        {
+            if (cudaMemcpyAsync(d_ooff, h_ooff.data(), ((size_t) nb + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) return 4;
+            BRA_LAUNCH(P_GLUE, st, compact_out_kernel<<<dim3(bra_div_up(S, 4096), nb), 256, 0, st>>>(d_out, S, d_len, d_ooff, d_cmp));
+            src = d_cmp;
+        }
+        if (cudaMemcpyAsync(out + produced, src, o, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
+        produced += o;
+        pos = p;
+    }
+    *out_size = produced;
+    if (crc_chain) *crc_chain = crc;
+    return 0;
+}
+
+// ---- synthetic workloads ------------------------------------------------------
+static inline uint64_t splitmix64(uint64_t& s)
+{
+    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
+    z          = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z          = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+extern "C" void bra_b200_gen_random(uint8_t* out, uint64_t n, uint64_t seed)
+{
+    uint64_t s = seed, i = 0;
+    for (; i + 8 <= n; i += 8)
+    {
+        const uint64_t v = splitmix64(s);
+        memcpy(out + i, &v, 8);  // little-endian bytes of successive outputs
+    }
+    if (i < n)
+    {
+        const uint64_t v = splitmix64(s);
+        memcpy(out + i, &v, n - i);
+    }
+}
+
+extern "C" void bra_b200_gen_text(uint8_t* out, uint64_t n, uint64_t seed, const char* const* vocab, uint32_t nvocab)
+{
+    uint64_t s = seed, i = 0;
+    if (nvocab == 0) return;
+    std::vector<uint32_t> wl(nvocab);
+    for (uint32_t k = 0; k < nvocab; ++k) wl[k] = (uint32_t) strlen(vocab[k]);
+    bool first = true;
+    while (i < n)
+    {
+        if (!first) out[i++] = ' ';
+        first = false;
+        if (i >= n) break;
+        const uint32_t k = (uint32_t) (splitmix64(s) % nvocab);
+        const uint64_t m = std::min<uint64_t>(wl[k], n - i);
+        memcpy(out + i, vocab[k], m);
+        i += m;
+    }
+}
+
+extern "C" void bra_b200_gen_periodic(uint8_t* out, uint64_t n, const uint8_t* pattern, uint32_t plen)
+{
+    if (plen == 0) return;
+    for (uint64_t i = 0; i < n; i += plen) memcpy(out + i, pattern, (size_t) std::min<uint64_t>(plen, n - i));
+}

@@ -1,0 +1,581 @@
+// huffman.cu -- canonical Huffman coding for a batch of blocks
+// (replaces reference bra_huffman_encode / bra_huffman_decode, src/encoders/bra_huffman.c:352-498).
+//
+// ENCODE
+//   histogram  : 256 bins per block (produced by the RLE emit kernel on the fused path, or by
+//                huf_hist_kernel for the stand-alone API), shared-memory privatised per CTA.
+//   build      : one thread per block replays the reference's sorted-list tree build exactly
+//                (bra_hd.h: bra_huf_build_lengths) -- code lengths depend on its tie rule, so no
+//                "optimal lengths" algorithm may be substituted -- then assigns canonical codes.
+//   bit lengths: per 4096-symbol tile, sum of code lengths; per-block exclusive scan gives every
+//                tile its first output bit (and the block its encoded_size).
+//   pack       : each thread owns 16 consecutive symbols, an exclusive prefix sum over code
+//                lengths gives its bit offset; codewords are OR-ed MSB-first into a shared-memory
+//                image of the tile's output words, which then leaves with coalesced word stores
+//                (the two words shared with neighbouring tiles by atomicOr).
+// DECODE (the format has no sync markers: bra_huffman_t is lengths + two sizes, lib_bra_types.h:51-56)
+//   Self-synchronising decode: the payload is cut into 128-bit subsequences, one per thread,
+//   256 per CTA. Every thread decodes from its current guess of where the first codeword of
+//   its subsequence starts and publishes where it crossed into the next subsequence; guesses
+//   are refined by fixed-point iteration (in shared memory inside the CTA, across CTAs by
+//   re-launching while any CTA's entry changed). Subsequence 0 starts at bit 0, so the fixed
+//   point is the true parse. Symbol counts are scanned and a second pass writes the output.
+#include "bra_common.cuh"
+#include "bra_hd.h"
+#include "bra_kernels.h"
+
+namespace bra {
+
+#define HF_TILE 4096
+#define HF_THREADS 256
+
+// ------------------------------------------------------------------------------------------------
+// histogram (stand-alone path)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HF_THREADS)
+    huf_hist_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len, uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t h[256];
+    const uint32_t      b = blockIdx.y;
+    const uint32_t      n = len[b];
+    const uint32_t      tile0 = blockIdx.x * HF_TILE;
+    if (tile0 >= n) return;
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint8_t* p    = in + (uint64_t) b * stride;
+    const uint32_t tend = min(n, tile0 + HF_TILE);
+    for (uint32_t i = tile0 + threadIdx.x; i < tend; i += HF_THREADS) atomicAdd(&h[p[i]], 1u);
+    __syncthreads();
+    if (h[threadIdx.x]) atomicAdd(&hist[(uint64_t) b * 256 + threadIdx.x], h[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// tree build + canonical codes + header fields. One thread per block (tiny, branchy work).
+// hdr layout (268 bytes, reference lib_bra_types.h:63-68): u32 primary | lengths[256] | u32 orig | u32 enc
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+    huf_build_kernel(const uint32_t* __restrict__ hist, const uint32_t* __restrict__ rlen, uint8_t* __restrict__ hdr, uint32_t* __restrict__ codes,
+                     uint32_t* __restrict__ ok)
+{
+    __shared__ bra_huf_build_ws_t ws;
+    __shared__ uint8_t            lengths[256];
+    const uint32_t                b = blockIdx.x;
+    if (threadIdx.x == 0)
+    {
+        const uint32_t k = bra_huf_build_lengths(hist + (uint64_t) b * 256, lengths, &ws);
+        ok[b]            = k != 0 && rlen[b] != 0;  // empty input: reference returns NULL (bra_huffman.c:155-156)
+        bra_huf_canonical(lengths, codes + (uint64_t) b * 256);
+    }
+    __syncwarp();
+    uint8_t* h = hdr + (uint64_t) b * 268;
+    for (int i = threadIdx.x; i < 256; i += 32) h[4 + i] = lengths[i];
+    if (threadIdx.x == 0)
+    {
+        const uint32_t r = rlen[b];
+        h[260] = (uint8_t) r;
+        h[261] = (uint8_t) (r >> 8);
+        h[262] = (uint8_t) (r >> 16);
+        h[263] = (uint8_t) (r >> 24);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bits per tile, then per-block scan
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(HF_THREADS)
+    huf_tile_bits_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ rlen, const uint8_t* __restrict__ hdr,
+                         uint32_t tiles, uint32_t* __restrict__ t_bits)
+{
+    __shared__ uint8_t  slen[256];
+    __shared__ uint32_t red[34];
+    const uint32_t      b = blockIdx.y, t = blockIdx.x;
+    const uint32_t      r = rlen[b];
+    const uint32_t      tile0 = t * HF_TILE;
+    if (tile0 >= r) return;
+    slen[threadIdx.x] = hdr[(uint64_t) b * 268 + 4 + threadIdx.x];
+    __syncthreads();
+    const uint8_t* p    = in + (uint64_t) b * stride;
+    const uint32_t tend = min(r, tile0 + HF_TILE);
+    uint32_t       s    = 0;
+    for (uint32_t i = tile0 + threadIdx.x; i < tend; i += HF_THREADS) s += slen[p[i]];
+    uint32_t total;
+    block_excl_add(s, red, &total);
+    if (threadIdx.x == 0) t_bits[(uint64_t) b * tiles + t] = total;
+}
+
+// exclusive scan of t_bits per block (in place) + encoded_size into the header
+__global__ void __launch_bounds__(256)
+    huf_scan_bits_kernel(uint32_t* __restrict__ t_bits, const uint32_t* __restrict__ rlen, uint32_t tiles, uint8_t* __restrict__ hdr,
+                         uint32_t* __restrict__ clen)
+{
+    __shared__ uint32_t red[34];
+    const uint32_t      b = blockIdx.x;
+    const uint32_t      r = rlen[b];
+    const uint32_t      ntiles = (r + HF_TILE - 1) / HF_TILE;
+    uint32_t*           tb     = t_bits + (uint64_t) b * tiles;
+    uint32_t            carry  = 0;
+    for (uint32_t base = 0; base < ntiles; base += 256)
+    {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < ntiles ? tb[i] : 0u;
+        uint32_t       tot;
+        const uint32_t ex = block_excl_add(v, red, &tot) + carry;
+        if (i < ntiles) tb[i] = ex;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        const uint32_t c = (carry + 7u) / 8u;  // uint32 arithmetic like bra_huffman.c:390-395
+        clen[b]          = c;
+        uint8_t* h       = hdr + (uint64_t) b * 268;
+        h[264] = (uint8_t) c;
+        h[265] = (uint8_t) (c >> 8);
+        h[266] = (uint8_t) (c >> 16);
+        h[267] = (uint8_t) (c >> 24);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pack. Output words are big-endian images of the byte stream (bit 31 = first bit), byte-swapped
+// on the way out. Max 34 bits per code (uint32 code, zero-extended like the reference's bit array).
+// ------------------------------------------------------------------------------------------------
+#define HF_WORDS (HF_TILE * 34 / 32 + 8)
+
+__device__ __forceinline__ void huf_put(uint32_t* img, uint32_t bitpos, uint64_t code, uint32_t len)
+{
+    // code occupies `len` (<= 40) bits, MSB first, starting at stream bit `bitpos`
+    while (len)
+    {
+        const uint32_t w    = bitpos >> 5, o = bitpos & 31u;
+        const uint32_t room = 32u - o;
+        const uint32_t take = len < room ? len : room;
+        const uint32_t bits = (uint32_t) ((code >> (len - take)) & ((take == 32u) ? 0xFFFFFFFFull : ((1ull << take) - 1ull)));
+        atomicOr(&img[w], bits << (room - take));
+        bitpos += take;
+        len -= take;
+    }
+}
+
+__global__ void __launch_bounds__(HF_THREADS)
+    huf_pack_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ rlen, const uint8_t* __restrict__ hdr,
+                    const uint32_t* __restrict__ codes, uint32_t tiles, const uint32_t* __restrict__ t_bitoff, uint8_t* __restrict__ out,
+                    uint64_t out_stride)
+{
+    __shared__ uint8_t  slen[256];
+    __shared__ uint32_t scode[256];
+    __shared__ uint32_t img[HF_WORDS];
+    __shared__ uint32_t red[34];
+    const uint32_t      b = blockIdx.y, t = blockIdx.x;
+    const uint32_t      r = rlen[b];
+    const uint32_t      tile0 = t * HF_TILE;
+    if (tile0 >= r) return;
+    slen[threadIdx.x]  = hdr[(uint64_t) b * 268 + 4 + threadIdx.x];
+    scode[threadIdx.x] = codes[(uint64_t) b * 256 + threadIdx.x];
+    for (int i = threadIdx.x; i < HF_WORDS; i += HF_THREADS) img[i] = 0;
+    __syncthreads();
+
+    const uint8_t* p  = in + (uint64_t) b * stride;
+    const uint32_t j0 = tile0 + threadIdx.x * 16;
+    const uint32_t m  = j0 < r ? min(16u, r - j0) : 0u;
+    uint8_t        x[16];
+    uint32_t       mybits = 0;
+    if (m == 16)
+    {
+        const uint4    v    = *reinterpret_cast<const uint4*>(p + j0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) x[i] = (uint32_t) i < m ? p[j0 + i] : 0;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if ((uint32_t) i < m) mybits += slen[x[i]];
+    uint32_t       tile_bits;
+    uint32_t       off   = block_excl_add(mybits, red, &tile_bits);
+    const uint32_t gbit0 = t_bitoff[(uint64_t) b * tiles + t];  // first bit of the tile in the block's stream
+    const uint32_t skew  = gbit0 & 31u;                         // image word 0 == global word gbit0/32
+    off += skew;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+    {
+        if ((uint32_t) i >= m) break;
+        const uint32_t l = slen[x[i]];
+        huf_put(img, off, (uint64_t) scode[x[i]], l);
+        off += l;
+    }
+    __syncthreads();
+
+    const uint32_t nwords = (skew + tile_bits + 31u) >> 5;
+    uint32_t*      ow     = reinterpret_cast<uint32_t*>(out + (uint64_t) b * out_stride) + (gbit0 >> 5);
+    for (uint32_t i = threadIdx.x; i < nwords; i += HF_THREADS)
+    {
+        const uint32_t v = __byte_perm(img[i], 0, 0x0123);  // big-endian image -> little-endian store
+        if (i == 0 || i + 1 == nwords)
+        {
+            if (v) atomicOr(&ow[i], v);  // word shared with the neighbouring tile
+        }
+        else
+            ow[i] = v;
+    }
+}
+
+bool huf_encode_batch(const HufEncArgs& a, cudaStream_t st)
+{
+    if (a.nblk == 0 || a.max_r == 0) return true;
+    const uint32_t tiles = bra_div_up(a.max_r, HF_TILE);
+    const dim3     grid(tiles, a.nblk);
+    if (a.compute_hist)
+    {
+        BRA_CUDA_TRY(cudaMemsetAsync(a.d_hist, 0, (size_t) a.nblk * 256 * 4, st));
+        BRA_LAUNCH(P_HUF_HIST, st, huf_hist_kernel<<<grid, HF_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, a.d_hist));
+    }
+    BRA_LAUNCH(P_HUF_BUILD, st, huf_build_kernel<<<a.nblk, 32, 0, st>>>(a.d_hist, a.d_rlen, a.d_hdr, a.d_codes, a.d_ok));
+    BRA_LAUNCH(P_HUF_BITS, st, huf_tile_bits_kernel<<<grid, HF_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, a.d_hdr, tiles, a.d_t_bits));
+    BRA_LAUNCH(P_HUF_BITS, st, huf_scan_bits_kernel<<<a.nblk, 256, 0, st>>>(a.d_t_bits, a.d_rlen, tiles, a.d_hdr, a.d_clen));
+    BRA_CUDA_TRY(cudaMemsetAsync(a.d_out, 0, (size_t) a.nblk * a.out_stride, st));
+    BRA_LAUNCH(P_HUF_PACK, st, huf_pack_kernel<<<grid, HF_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, a.d_hdr, a.d_codes, tiles, a.d_t_bits, a.d_out, a.out_stride));
+    BRA_CUDA_TRY(cudaGetLastError());
+    return true;
+}
+
+// ================================================================================================
+// DECODE
+// ================================================================================================
+#define HD_SUB_BITS 128u
+#define HD_THREADS 256
+#define HD_SEQ_BITS (HD_SUB_BITS * HD_THREADS)  // 32768 bits = 4 KiB of payload per CTA
+#define HD_SEQ_BYTES (HD_SEQ_BITS / 8)
+#define HD_SMEM_WORDS (HD_SEQ_BYTES / 4 + 4)    // + look-ahead for codes crossing the sequence end
+
+// per-block decode tables, built once per block by one thread
+__global__ void __launch_bounds__(32) huf_dec_tables_kernel(const uint8_t* __restrict__ hdr, bra_huf_dec_t* __restrict__ tabs, uint32_t* __restrict__ err)
+{
+    __shared__ uint8_t lengths[256];
+    const uint32_t     b = blockIdx.x;
+    for (int i = threadIdx.x; i < 256; i += 32) lengths[i] = hdr[(uint64_t) b * 268 + 4 + i];
+    __syncwarp();
+    if (threadIdx.x == 0)
+    {
+        if (!bra_huf_make_dec(lengths, &tabs[b])) err[b] = 1;
+    }
+}
+
+// big-endian 32-bit window starting at bit `pos` of the CTA's staged payload words
+__device__ __forceinline__ uint32_t hd_peek(const uint32_t* sw, uint32_t pos)
+{
+    const uint32_t w = pos >> 5, o = pos & 31u;
+    const uint32_t a = sw[w], b2 = sw[w + 1];
+    return o ? (a << o) | (b2 >> (32u - o)) : a;
+}
+
+struct HdShared
+{
+    uint32_t      words[HD_SMEM_WORDS];
+    bra_huf_dec_t tab;
+    uint32_t      start[HD_THREADS + 1];  // bit offset (relative to the sequence start) of the first codeword of each subsequence
+    uint32_t      red[34];
+    int           changed;
+};
+
+__device__ __forceinline__ void hd_stage(HdShared& S, const uint8_t* __restrict__ pay, uint32_t seq, uint32_t cbytes)
+{
+    // stage this CTA's payload slice (+ look-ahead) as big-endian words; bytes past the payload read as 0
+    const uint32_t  byte0 = seq * HD_SEQ_BYTES;
+    const uint32_t* pw    = reinterpret_cast<const uint32_t*>(pay) + byte0 / 4;
+    for (uint32_t i = threadIdx.x; i < HD_SMEM_WORDS; i += HD_THREADS)
+    {
+        const uint32_t bo = byte0 + i * 4;
+        uint32_t       v  = 0;
+        if (bo < cbytes)
+        {
+            v = __byte_perm(pw[i], 0, 0x0123);
+            if (bo + 4 > cbytes) v &= 0xFFFFFFFFu << ((bo + 4 - cbytes) * 8);
+        }
+        S.words[i] = v;
+    }
+}
+
+// Decode subsequence k from relative bit `pos` until crossing its end (or the end of the payload).
+// Returns the exit position; *count = number of complete codewords that START inside [pos, end).
+// A bit pattern that matches no codeword stops the walk (dead speculative path or corrupt data).
+__device__ __forceinline__ uint32_t hd_walk(const HdShared& S, uint32_t pos, uint32_t sub_end, uint32_t data_end, uint32_t* count, bool* dead)
+{
+    uint32_t c = 0;
+    *dead      = false;
+    while (pos < sub_end && pos < data_end)
+    {
+        uint8_t        sym;
+        const uint32_t l = bra_huf_decode_one(&S.tab, hd_peek(S.words, pos), &sym);
+        if (l == 0)
+        {
+            *dead = true;
+            break;
+        }
+        if (pos + l > data_end) break;  // incomplete trailing code: padding
+        pos += l;
+        ++c;
+    }
+    *count = c;
+    return pos;
+}
+
+// One synchronisation sweep. sub_start/sub_count persist between launches.
+//   seq_entry[b][seq] : entry bit offset this CTA last used (0xFFFFFFFF = never ran)
+//   seq_exit[b][seq]  : where its last subsequence crossed into the next CTA's sequence (relative to that sequence)
+__global__ void __launch_bounds__(HD_THREADS)
+    huf_dec_sync_kernel(const uint8_t* __restrict__ pay, uint64_t pay_stride, const uint32_t* __restrict__ clen, const bra_huf_dec_t* __restrict__ tabs,
+                        const uint32_t* __restrict__ err, uint32_t seqs, uint8_t* __restrict__ sub_start, uint8_t* __restrict__ sub_count,
+                        uint32_t* __restrict__ seq_entry, uint32_t* __restrict__ seq_exit, uint32_t* __restrict__ seq_count,
+                        uint32_t* __restrict__ changed_flag)
+{
+    __shared__ HdShared S;
+    const uint32_t      b = blockIdx.y, seq = blockIdx.x;
+    const uint32_t      c = clen[b];
+    if ((uint64_t) seq * HD_SEQ_BYTES >= c || err[b]) return;
+    const uint64_t sidx = (uint64_t) b * seqs + seq;
+    // seq_exit of the left neighbour may be rewritten by that CTA during this very launch: read it
+    // once and broadcast, so that the whole CTA takes the same decision.
+    __shared__ uint32_t s_entry, s_prev;
+    if (threadIdx.x == 0)
+    {
+        s_entry = seq == 0 ? 0u : *reinterpret_cast<volatile const uint32_t*>(&seq_exit[sidx - 1]);
+        s_prev  = seq_entry[sidx];
+    }
+    __syncthreads();
+    const uint32_t entry = s_entry;
+    if (s_prev == entry) return;  // nothing upstream changed since this CTA last ran
+
+    const bool first_run = s_prev == 0xFFFFFFFFu;
+    for (uint32_t i = threadIdx.x; i < sizeof(bra_huf_dec_t) / 4; i += HD_THREADS)
+        reinterpret_cast<uint32_t*>(&S.tab)[i] = reinterpret_cast<const uint32_t*>(&tabs[b])[i];
+    hd_stage(S, pay + (uint64_t) b * pay_stride, seq, c);
+    const uint32_t k        = threadIdx.x;
+    const uint64_t sub_idx  = sidx * HD_THREADS + k;
+    const uint32_t data_end = min((uint32_t) HD_SEQ_BITS + 64u, (c - seq * HD_SEQ_BYTES) * 8u);  // relative bit where the payload ends
+    // current guess for this subsequence's first codeword
+    S.start[k] = first_run ? k * HD_SUB_BITS : k * HD_SUB_BITS + sub_start[sub_idx];
+    if (k == 0)
+    {
+        S.start[0]          = entry;
+        S.start[HD_THREADS] = first_run ? HD_SEQ_BITS : HD_SEQ_BITS + seq_exit[sidx];
+    }
+    __syncthreads();
+
+    uint32_t used  = 0xFFFFFFFFu;  // start value my current (exit, count) were computed from
+    uint32_t myexit = 0, mycount = 0;
+    if (!first_run && k != 0)
+    {
+        // state from the previous launch is still valid unless my start changes
+        used    = S.start[k];
+        myexit  = S.start[k + 1];
+        mycount = sub_count[sub_idx];
+    }
+    for (int it = 0; it < HD_THREADS + 2; ++it)
+    {
+        const uint32_t st = S.start[k];
+        bool           ch = false;
+        uint32_t       nx = myexit;
+        if (st != used)
+        {
+            bool dead;
+            nx   = hd_walk(S, st, (k + 1) * HD_SUB_BITS, data_end, &mycount, &dead);
+            if (dead || nx < (k + 1) * HD_SUB_BITS) nx = (k + 1) * HD_SUB_BITS;  // dead path / payload ended: neutral guess
+            used   = st;
+            myexit = nx;
+        }
+        __syncthreads();
+        if (S.start[k + 1] != nx)
+        {
+            S.start[k + 1] = nx;
+            ch             = true;
+        }
+        if (!__syncthreads_or(ch)) break;
+    }
+    sub_start[sub_idx] = (uint8_t) (S.start[k] - k * HD_SUB_BITS);
+    sub_count[sub_idx] = (uint8_t) mycount;
+    uint32_t total;
+    block_excl_add(mycount, S.red, &total);
+    if (k == 0)
+    {
+        seq_entry[sidx] = entry;
+        seq_count[sidx] = total;
+        const uint32_t ex = S.start[HD_THREADS] - HD_SEQ_BITS;
+        if (first_run || seq_exit[sidx] != ex)
+        {
+            seq_exit[sidx] = ex;
+            atomicAdd(changed_flag, 1u);
+        }
+    }
+}
+
+// exclusive scan of symbol counts over the sequences of a block; checks total >= orig_size
+__global__ void __launch_bounds__(256)
+    huf_dec_scan_kernel(uint32_t* __restrict__ seq_count, const uint32_t* __restrict__ clen, const uint8_t* __restrict__ hdr, uint32_t seqs,
+                        uint32_t* __restrict__ err)
+{
+    __shared__ uint32_t red[34];
+    const uint32_t      b = blockIdx.x;
+    if (err[b]) return;
+    const uint32_t c     = clen[b];
+    const uint32_t nseq  = (c + HD_SEQ_BYTES - 1) / HD_SEQ_BYTES;
+    uint32_t*      sc    = seq_count + (uint64_t) b * seqs;
+    uint32_t       carry = 0;
+    for (uint32_t base = 0; base < nseq; base += 256)
+    {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nseq ? sc[i] : 0u;
+        uint32_t       tot;
+        const uint32_t ex = block_excl_add(v, red, &tot) + carry;
+        if (i < nseq) sc[i] = ex;
+        carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        const uint8_t* h    = hdr + (uint64_t) b * 268;
+        const uint32_t orig = (uint32_t) h[260] | ((uint32_t) h[261] << 8) | ((uint32_t) h[262] << 16) | ((uint32_t) h[263] << 24);
+        if (carry < orig) err[b] = 1;  // ran out of data (bra_huffman.c:485-489)
+    }
+}
+
+// Second pass: every subsequence decodes again from its synchronised start and stores its symbols.
+// The thread that writes symbol orig_size-1 records the bit position just after it.
+__global__ void __launch_bounds__(HD_THREADS)
+    huf_dec_write_kernel(const uint8_t* __restrict__ pay, uint64_t pay_stride, const uint32_t* __restrict__ clen, const uint8_t* __restrict__ hdr,
+                         const bra_huf_dec_t* __restrict__ tabs, uint32_t seqs, const uint8_t* __restrict__ sub_start,
+                         const uint8_t* __restrict__ sub_count, const uint32_t* __restrict__ seq_off, uint8_t* __restrict__ out,
+                         uint64_t out_stride, uint32_t* __restrict__ end_bit, uint32_t* __restrict__ err)
+{
+    __shared__ HdShared S;
+    const uint32_t      b = blockIdx.y, seq = blockIdx.x;
+    const uint32_t      c = clen[b];
+    if ((uint64_t) seq * HD_SEQ_BYTES >= c || err[b]) return;
+    const uint8_t* h    = hdr + (uint64_t) b * 268;
+    const uint32_t orig = (uint32_t) h[260] | ((uint32_t) h[261] << 8) | ((uint32_t) h[262] << 16) | ((uint32_t) h[263] << 24);
+    const uint64_t sidx = (uint64_t) b * seqs + seq;
+    const uint32_t o0   = seq_off[sidx];
+    if (o0 >= orig) return;  // everything here is padding
+    for (uint32_t i = threadIdx.x; i < sizeof(bra_huf_dec_t) / 4; i += HD_THREADS)
+        reinterpret_cast<uint32_t*>(&S.tab)[i] = reinterpret_cast<const uint32_t*>(&tabs[b])[i];
+    hd_stage(S, pay + (uint64_t) b * pay_stride, seq, c);
+    const uint32_t k       = threadIdx.x;
+    const uint64_t sub_idx = sidx * HD_THREADS + k;
+    const uint32_t cnt     = sub_count[sub_idx];
+    uint32_t       dummy;
+    uint32_t       o   = o0 + block_excl_add(cnt, S.red, &dummy);  // also orders the staging writes
+    uint32_t       pos = k * HD_SUB_BITS + sub_start[sub_idx];
+    uint8_t*       ob  = out + (uint64_t) b * out_stride;
+    const uint32_t sub_end  = (k + 1) * HD_SUB_BITS;
+    const uint32_t data_end = min((uint32_t) HD_SEQ_BITS + 64u, (c - seq * HD_SEQ_BYTES) * 8u);
+    // same walk as hd_walk (so the counts agree), now storing the symbols
+    while (pos < sub_end && pos < data_end && o < orig)
+    {
+        uint8_t        sym = 0;
+        const uint32_t l   = bra_huf_decode_one(&S.tab, hd_peek(S.words, pos), &sym);
+        if (l == 0)
+        {
+            err[b] = 1;  // no codeword matches before orig_size symbols: "invalid code sequence" (bra_huffman.c:466-470)
+            break;
+        }
+        if (pos + l > data_end) break;
+        ob[o++] = sym;
+        pos += l;
+        if (o == orig) end_bit[b] = seq * HD_SEQ_BITS + pos;
+    }
+}
+
+// Bytes after the one holding the last symbol: the reference keeps walking them from the tree root
+// (bra_huffman.c:455-481) and fails if that walk completes a codeword or leaves the tree.
+__global__ void huf_dec_trailing_kernel(const uint8_t* __restrict__ pay, uint64_t pay_stride, const uint32_t* __restrict__ clen,
+                                        const bra_huf_dec_t* __restrict__ tabs, const uint32_t* __restrict__ end_bit, uint32_t* __restrict__ err,
+                                        uint32_t nblk)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk || err[b]) return;
+    const uint32_t       c    = clen[b];
+    const uint32_t       from = (end_bit[b] + 7u) / 8u;  // first byte the reference's outer loop visits next
+    if (from >= c) return;
+    const bra_huf_dec_t* d = &tabs[b];
+    const uint8_t*       p = pay + (uint64_t) b * pay_stride;
+    // bit-by-bit walk with exact tree semantics: prefix v of depth dep is a node iff some code of
+    // length L >= dep has it as a prefix; it is a leaf iff L == dep.
+    uint32_t v = 0, dep = 0;
+    for (uint32_t i = from; i < c; ++i)
+        for (int bit = 7; bit >= 0; --bit)
+        {
+            v = (v << 1) | ((p[i] >> bit) & 1u);
+            ++dep;
+            bool node = false, leaf = false;
+            if (dep <= d->max_len)
+                for (uint32_t L = dep; L <= d->max_len; ++L)
+                {
+                    if (!d->count[L]) continue;
+                    const uint32_t lo = d->first[L] >> (L - dep), hi = (d->first[L] + d->count[L] - 1) >> (L - dep);
+                    if (v >= lo && v <= hi)
+                    {
+                        node = true;
+                        leaf = (L == dep);
+                        break;
+                    }
+                }
+            if (!node || leaf)
+            {
+                err[b] = 1;  // left the tree, or decoded a symbol beyond orig_size
+                return;
+            }
+        }
+}
+
+bool huf_decode_batch(const HufDecArgs& a, cudaStream_t st)
+{
+    if (a.nblk == 0 || a.max_c == 0) return true;
+    const uint32_t seqs = bra_div_up(a.max_c, HD_SEQ_BYTES);
+    const dim3     grid(seqs, a.nblk);
+    BRA_LAUNCH(P_HUF_DEC_TABLES, st, huf_dec_tables_kernel<<<a.nblk, 32, 0, st>>>(a.d_hdr, a.d_tabs, a.d_err));
+    BRA_CUDA_TRY(cudaMemsetAsync(a.d_seq_entry, 0xFF, (size_t) a.nblk * seqs * 4, st));
+    BRA_CUDA_TRY(cudaMemsetAsync(a.d_seq_exit, 0, (size_t) a.nblk * seqs * 4, st));  // first guess: codewords start on sequence boundaries
+    BRA_CUDA_TRY(cudaMemsetAsync(a.d_end_bit, 0, (size_t) a.nblk * 4, st));
+    uint32_t sweeps = 0;
+    for (;;)
+    {
+        BRA_CUDA_TRY(cudaMemsetAsync(a.d_changed, 0, 4, st));
+        for (int rep = 0; rep < 2; ++rep)
+            BRA_LAUNCH(P_HUF_DEC_SYNC, st, huf_dec_sync_kernel<<<grid, HD_THREADS, 0, st>>>(a.d_pay, a.pay_stride, a.d_clen, a.d_tabs, a.d_err, seqs, a.d_sub_start,
+                                                             a.d_sub_count, a.d_seq_entry, a.d_seq_exit, a.d_seq_count, a.d_changed));
+        sweeps += 2;
+        uint32_t changed = 0;
+        BRA_CUDA_TRY(cudaMemcpyAsync(&changed, a.d_changed, 4, cudaMemcpyDeviceToHost, st));
+        BRA_CUDA_TRY(cudaStreamSynchronize(st));
+        // the first pair of sweeps always reports changes (every CTA publishes its first exit)
+        if (changed == 0 || sweeps > 2 * seqs + 4) break;
+        if (sweeps == 2)
+        {
+            // cheap confirmation sweep: if nothing moves any more we are at the fixed point
+            BRA_CUDA_TRY(cudaMemsetAsync(a.d_changed, 0, 4, st));
+            BRA_LAUNCH(P_HUF_DEC_SYNC, st, huf_dec_sync_kernel<<<grid, HD_THREADS, 0, st>>>(a.d_pay, a.pay_stride, a.d_clen, a.d_tabs, a.d_err, seqs, a.d_sub_start,
+                                                             a.d_sub_count, a.d_seq_entry, a.d_seq_exit, a.d_seq_count, a.d_changed));
+            ++sweeps;
+            BRA_CUDA_TRY(cudaMemcpyAsync(&changed, a.d_changed, 4, cudaMemcpyDeviceToHost, st));
+            BRA_CUDA_TRY(cudaStreamSynchronize(st));
+            if (changed == 0) break;
+        }
+    }
+    if (a.h_sweeps) *a.h_sweeps = sweeps;
+    BRA_LAUNCH(P_HUF_DEC_SCAN, st, huf_dec_scan_kernel<<<a.nblk, 256, 0, st>>>(a.d_seq_count, a.d_clen, a.d_hdr, seqs, a.d_err));
+    BRA_LAUNCH(P_HUF_DEC_WRITE, st, huf_dec_write_kernel<<<grid, HD_THREADS, 0, st>>>(a.d_pay, a.pay_stride, a.d_clen, a.d_hdr, a.d_tabs, seqs, a.d_sub_start, a.d_sub_count,
+                                                      a.d_seq_count, a.d_out, a.out_stride, a.d_end_bit, a.d_err));
+    BRA_LAUNCH(P_HUF_DEC_TRAILING, st, huf_dec_trailing_kernel<<<bra_div_up(a.nblk, 64), 64, 0, st>>>(a.d_pay, a.pay_stride, a.d_clen, a.d_tabs, a.d_end_bit, a.d_err, a.nblk));
+    BRA_CUDA_TRY(cudaGetLastError());
+    return true;
+}
+
+uint32_t huf_enc_tiles(uint32_t max_r) { return bra_div_up(max_r, HF_TILE); }
+uint32_t huf_dec_seqs(uint32_t max_c) { return bra_div_up(max_c, HD_SEQ_BYTES); }
+uint32_t huf_dec_subs_per_seq() { return HD_THREADS; }
+
+}  // namespace bra

@@ -1,0 +1,296 @@
+// mtf.cu -- move-to-front coding and decoding for a batch of blocks
+// (replaces reference bra_mtf_encode2 / bra_mtf_decode2, src/encoders/bra_mtf.c:67-82, :98-115).
+//
+// The reference walks the block with one 256-entry list (identity at block start,
+// bra_mtf.c:9-13). Here every block is cut into 4 KiB segments that run in parallel:
+//   summary : what a segment does to ANY incoming list, without knowing it
+//               encode -> the segment's distinct symbols in most-recent-first order
+//               decode -> the permutation of list positions the segment's ranks perform
+//   scan    : per block, compose the summaries left to right -> the list entering each segment
+//   apply   : replay each segment from its entry list.
+// The list lives in registers, 8 entries per lane of a warp; one symbol costs a byte-compare,
+// a ballot and a funnel shift across lanes, independent of the rank (random data has mean rank
+// ~128, which is what makes the reference's linear search slow).
+// Traffic: read n + write n (+ 256 B of state per 4 KiB segment, twice). Latency/issue bound.
+#include "bra_common.cuh"
+#include "bra_kernels.h"
+
+namespace bra {
+
+#define MTF_SEG 4096
+#define MTF_WARPS 4  // warps (= segments) per CTA
+
+// ---- warp-resident list: lane l holds entries 8l..8l+7, entry 8l in the low byte of `lo` --------
+struct WarpList
+{
+    uint32_t lo, hi;
+};
+
+__device__ __forceinline__ WarpList wl_identity()
+{
+    const uint32_t b = lane_id() * 8;
+    WarpList       r;
+    r.lo = (b) | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24);
+    r.hi = (b + 4) | ((b + 5) << 8) | ((b + 6) << 16) | ((b + 7) << 24);
+    return r;
+}
+__device__ __forceinline__ WarpList wl_load(const uint8_t* p)  // 256 bytes, 8-byte aligned
+{
+    const uint2 v = reinterpret_cast<const uint2*>(p)[lane_id()];
+    WarpList    r;
+    r.lo = v.x;
+    r.hi = v.y;
+    return r;
+}
+__device__ __forceinline__ void wl_store(uint8_t* p, WarpList l) { reinterpret_cast<uint2*>(p)[lane_id()] = make_uint2(l.lo, l.hi); }
+
+// Move the entry at list position `pos` (warp-uniform) to the front; `sym` is its value.
+__device__ __forceinline__ void wl_move_to_front(WarpList& L, uint32_t pos, uint32_t sym)
+{
+    const uint32_t lane = lane_id();
+    const uint32_t hl = pos >> 3, hb = pos & 7u;
+    // byte that enters this lane from the left neighbour (lane 0 receives the symbol itself)
+    uint32_t incoming = __shfl_up_sync(BRA_FULL, L.hi >> 24, 1);
+    if (lane == 0) incoming = sym;
+    const uint64_t v       = ((uint64_t) L.hi << 32) | L.lo;
+    const uint64_t shifted = (v << 8) | incoming;
+    uint64_t       nv      = v;
+    if (lane < hl)
+        nv = shifted;
+    else if (lane == hl)
+    {
+        const uint64_t keep = (hb == 7) ? 0ull : (~0ull << ((hb + 1) * 8));  // entries above the hit stay
+        nv                  = (v & keep) | (shifted & ~keep);
+    }
+    L.lo = (uint32_t) nv;
+    L.hi = (uint32_t) (nv >> 32);
+}
+
+// position of `sym` (warp-uniform) in the list
+__device__ __forceinline__ uint32_t wl_find(const WarpList& L, uint32_t sym)
+{
+    const uint32_t s4 = sym * 0x01010101u;
+    const uint32_t m0 = __vcmpeq4(L.lo, s4), m1 = __vcmpeq4(L.hi, s4);
+    const uint32_t ball = __ballot_sync(BRA_FULL, (m0 | m1) != 0u);
+    const uint32_t hl   = __ffs(ball) - 1;
+    const uint32_t in_lane = m0 ? ((__ffs(m0) - 1) >> 3) : (4 + ((__ffs(m1) - 1) >> 3));
+    return hl * 8 + __shfl_sync(BRA_FULL, in_lane, hl);
+}
+// value at list position `pos` (warp-uniform)
+__device__ __forceinline__ uint32_t wl_get(const WarpList& L, uint32_t pos)
+{
+    const uint32_t w = (pos & 4u) ? L.hi : L.lo;
+    return __shfl_sync(BRA_FULL, (w >> ((pos & 3u) * 8)) & 0xFFu, pos >> 3);
+}
+
+// ---- segment replay (shared by summary/apply) ---------------------------------------------------
+// ENCODE: in = symbols, out = ranks. DECODE: in = ranks, out = symbols. out may be null (summary).
+template <bool ENCODE, bool WRITE>
+__device__ __forceinline__ void mtf_replay(WarpList& L, const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t m)
+{
+    const uint32_t lane = lane_id();
+    for (uint32_t base = 0; base < m; base += 128)
+    {
+        const uint32_t cnt = min(128u, m - base);
+        uint32_t       wrd = 0;
+        if (base + lane * 4 + 4 <= m)
+            wrd = *reinterpret_cast<const uint32_t*>(in + base + lane * 4);
+        else
+            for (uint32_t k = 0; k < 4; ++k)
+                if (base + lane * 4 + k < m) wrd |= (uint32_t) in[base + lane * 4 + k] << (8 * k);
+        uint32_t ow = 0;
+        for (uint32_t i = 0; i < cnt; ++i)
+        {
+            const uint32_t x = (__shfl_sync(BRA_FULL, wrd, i >> 2) >> ((i & 3u) * 8)) & 0xFFu;
+            uint32_t       res;
+            if (ENCODE)
+            {
+                res = wl_find(L, x);
+                wl_move_to_front(L, res, x);
+            }
+            else
+            {
+                res = wl_get(L, x);
+                wl_move_to_front(L, x, res);
+            }
+            if (WRITE && lane == (i >> 2)) ow |= res << ((i & 3u) * 8);
+        }
+        if (WRITE)
+        {
+            if (base + lane * 4 + 4 <= m)
+                *reinterpret_cast<uint32_t*>(out + base + lane * 4) = ow;
+            else
+                for (uint32_t k = 0; k < 4; ++k)
+                    if (base + lane * 4 + k < m) out[base + lane * 4 + k] = (ow >> (8 * k)) & 0xFFu;
+        }
+    }
+}
+
+// ---- summaries ------------------------------------------------------------------------------
+// encode: recency list of the segment's distinct symbols. Computed from last-occurrence positions
+// (no sequential dependence): order[r] = symbol with the r-th largest last occurrence; cnt = #distinct.
+__global__ void __launch_bounds__(MTF_WARPS * 32)
+    mtf_enc_summary_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len, uint32_t segs,
+                           uint8_t* __restrict__ summ /* [b][seg][256] */, uint16_t* __restrict__ scnt /* [b][seg] */)
+{
+    __shared__ int s_last[MTF_WARPS][256];
+    const uint32_t b = blockIdx.y, w = warp_id(), lane = lane_id();
+    const uint32_t seg = blockIdx.x * MTF_WARPS + w;
+    const uint32_t n   = len[b];
+    if ((uint64_t) seg * MTF_SEG >= n) return;  // whole warps leave; no CTA barrier below
+    const uint32_t m = min((uint32_t) MTF_SEG, n - seg * MTF_SEG);
+    const uint8_t* p = in + (uint64_t) b * stride + (uint64_t) seg * MTF_SEG;
+    int*           last = s_last[w];
+    for (int i = lane; i < 256; i += 32) last[i] = -1;
+    __syncwarp();
+    for (uint32_t i = lane * 4; i < m; i += 128)
+    {
+        if (i + 4 <= m)
+        {
+            const uint32_t v = *reinterpret_cast<const uint32_t*>(p + i);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) atomicMax(&last[(v >> (8 * k)) & 0xFFu], (int) (i + k));
+        }
+        else
+            for (uint32_t k = 0; i + k < m; ++k) atomicMax(&last[p[i + k]], (int) (i + k));
+    }
+    __syncwarp();
+    // rank each present symbol by counting symbols with a later last occurrence
+    uint8_t* o = summ + ((uint64_t) b * segs + seg) * 256;
+    uint32_t present = 0;
+    int      mine[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+    {
+        mine[k] = last[lane * 8 + k];
+        present += mine[k] >= 0;
+    }
+    uint32_t rk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < 256; ++s)
+    {
+        const int ls = last[s];  // broadcast read
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rk[k] += ls > mine[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        if (mine[k] >= 0) o[rk[k]] = (uint8_t) (lane * 8 + k);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) present += __shfl_xor_sync(BRA_FULL, present, d);
+    if (lane == 0) scnt[(uint64_t) b * segs + seg] = (uint16_t) present;
+}
+
+// decode: permutation of positions performed by the segment = replay from the identity list
+__global__ void __launch_bounds__(MTF_WARPS * 32)
+    mtf_dec_summary_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len, uint32_t segs,
+                           uint8_t* __restrict__ summ)
+{
+    const uint32_t b = blockIdx.y, w = warp_id();
+    const uint32_t seg = blockIdx.x * MTF_WARPS + w;
+    const uint32_t n   = len[b];
+    if ((uint64_t) seg * MTF_SEG >= n) return;
+    const uint32_t m = min((uint32_t) MTF_SEG, n - seg * MTF_SEG);
+    WarpList       L = wl_identity();
+    mtf_replay<false, false>(L, in + (uint64_t) b * stride + (uint64_t) seg * MTF_SEG, nullptr, m);
+    wl_store(summ + ((uint64_t) b * segs + seg) * 256, L);
+}
+
+// ---- scan: one warp per block composes the summaries; state[b][seg] = list entering the segment ----
+template <bool ENCODE>
+__global__ void __launch_bounds__(32)
+    mtf_scan_kernel(const uint8_t* __restrict__ summ, const uint16_t* __restrict__ scnt, const uint32_t* __restrict__ len, uint32_t segs,
+                    uint8_t* __restrict__ state)
+{
+    __shared__ __align__(16) uint8_t cur[256];
+    __shared__ __align__(16) uint8_t nxt[256];
+    __shared__ __align__(16) uint8_t member[256];
+    const uint32_t b = blockIdx.x, lane = lane_id();
+    const uint32_t n = len[b];
+    const uint32_t nseg = (n + MTF_SEG - 1) / MTF_SEG;
+    for (int i = lane; i < 256; i += 32) cur[i] = (uint8_t) i;
+    __syncwarp();
+    for (uint32_t s = 0; s < nseg; ++s)
+    {
+        uint8_t*       st = state + ((uint64_t) b * segs + s) * 256;
+        const uint8_t* sm = summ + ((uint64_t) b * segs + s) * 256;
+        reinterpret_cast<uint2*>(st)[lane] = reinterpret_cast<const uint2*>(cur)[lane];
+        if (s + 1 == nseg) break;
+        if (ENCODE)
+        {
+            // new list = segment's recency list, then the old list minus those symbols (order kept)
+            const uint32_t k = scnt[(uint64_t) b * segs + s];
+            for (int i = lane; i < 256; i += 32) member[i] = 0;
+            __syncwarp();
+            for (uint32_t i = lane; i < k; i += 32)
+            {
+                const uint8_t sy = sm[i];
+                nxt[i]           = sy;
+                member[sy]       = 1;
+            }
+            __syncwarp();
+            uint32_t outp = k;
+            for (int r = 0; r < 8; ++r)
+            {
+                const uint8_t  sy   = cur[r * 32 + lane];
+                const bool     keep = !member[sy];
+                const uint32_t ball = __ballot_sync(BRA_FULL, keep);
+                if (keep) nxt[outp + __popc(ball & lanemask_lt())] = sy;
+                outp += __popc(ball);
+            }
+        }
+        else
+        {
+            // positions are permuted: new[j] = old[perm[j]]
+            for (int i = lane; i < 256; i += 32) nxt[i] = cur[sm[i]];
+        }
+        __syncwarp();
+        for (int i = lane; i < 256; i += 32) cur[i] = nxt[i];
+        __syncwarp();
+    }
+}
+
+// ---- apply ---------------------------------------------------------------------------------------
+template <bool ENCODE>
+__global__ void __launch_bounds__(MTF_WARPS * 32)
+    mtf_apply_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t stride, const uint32_t* __restrict__ len, uint32_t segs,
+                     const uint8_t* __restrict__ state)
+{
+    const uint32_t b = blockIdx.y, w = warp_id();
+    const uint32_t seg = blockIdx.x * MTF_WARPS + w;
+    const uint32_t n   = len[b];
+    if ((uint64_t) seg * MTF_SEG >= n) return;
+    const uint32_t m   = min((uint32_t) MTF_SEG, n - seg * MTF_SEG);
+    const uint64_t off = (uint64_t) b * stride + (uint64_t) seg * MTF_SEG;
+    WarpList       L   = wl_load(state + ((uint64_t) b * segs + seg) * 256);
+    mtf_replay<ENCODE, true>(L, in + off, out + off, m);
+}
+
+uint32_t mtf_segments(uint32_t max_n) { return bra_div_up(max_n, MTF_SEG); }
+
+bool mtf_encode_batch(const uint8_t* d_in, uint8_t* d_out, uint64_t stride, const uint32_t* d_len, uint32_t max_n, uint32_t nblk,
+                      uint8_t* d_summ, uint16_t* d_scnt, uint8_t* d_state, cudaStream_t st)
+{
+    if (nblk == 0 || max_n == 0) return true;
+    const uint32_t segs = mtf_segments(max_n);
+    const dim3     grid(bra_div_up(segs, MTF_WARPS), nblk);
+    BRA_LAUNCH(P_MTF_SUMMARY, st, mtf_enc_summary_kernel<<<grid, MTF_WARPS * 32, 0, st>>>(d_in, stride, d_len, segs, d_summ, d_scnt));
+    BRA_LAUNCH(P_MTF_SCAN, st, mtf_scan_kernel<true><<<nblk, 32, 0, st>>>(d_summ, d_scnt, d_len, segs, d_state));
+    BRA_LAUNCH(P_MTF_APPLY, st, mtf_apply_kernel<true><<<grid, MTF_WARPS * 32, 0, st>>>(d_in, d_out, stride, d_len, segs, d_state));
+    BRA_CUDA_TRY(cudaGetLastError());
+    return true;
+}
+
+bool mtf_decode_batch(const uint8_t* d_in, uint8_t* d_out, uint64_t stride, const uint32_t* d_len, uint32_t max_n, uint32_t nblk,
+                      uint8_t* d_summ, uint8_t* d_state, cudaStream_t st)
+{
+    if (nblk == 0 || max_n == 0) return true;
+    const uint32_t segs = mtf_segments(max_n);
+    const dim3     grid(bra_div_up(segs, MTF_WARPS), nblk);
+    BRA_LAUNCH(P_MTF_SUMMARY, st, mtf_dec_summary_kernel<<<grid, MTF_WARPS * 32, 0, st>>>(d_in, stride, d_len, segs, d_summ));
+    BRA_LAUNCH(P_MTF_SCAN, st, mtf_scan_kernel<false><<<nblk, 32, 0, st>>>(d_summ, nullptr, d_len, segs, d_state));
+    BRA_LAUNCH(P_MTF_APPLY, st, mtf_apply_kernel<false><<<grid, MTF_WARPS * 32, 0, st>>>(d_in, d_out, stride, d_len, segs, d_state));
+    BRA_CUDA_TRY(cudaGetLastError());
+    return true;
+}
+
+}  // namespace bra

@@ -1,0 +1,597 @@
+// rle.cu -- PackBits-style run-length coding for a batch of blocks
+// (replaces reference bra_rle_encode / bra_rle_decode / bra_rle_decode_compute_size,
+//  src/encoders/bra_rle.c:60-120, :162-224, :122-160; constants src/lib_bra_defs.h:95-98).
+//
+// ENCODE. The reference parses greedily, byte by byte. Its output has a closed form over the
+// maximal runs of the input (validated against the reference in tests/test_host_logic.py):
+//   * a run of length L >= 3 starting at s emits, for every k = 0,128,256,.. below L - rem,
+//     the token {1 - min(128, L - rem - k), value}; rem = L mod 128 if that is 1 or 2, else 0;
+//   * every other byte (runs of 1-2 bytes and the 1-2 leftover bytes of a long run) is a
+//     literal; maximal stretches of consecutive literals are cut from their start into groups
+//     of 128, each prefixed by {group_len - 1}.
+// So every byte knows what it emits once it knows (run start, run end, stretch start, stretch
+// end): four max/min scans of head positions plus a sum scan for the output offset. Four
+// streaming kernels per block, each recomputing the cheap per-byte state from the input and
+// taking its cross-tile carries from the tile summaries the previous kernel wrote:
+//   heads -> literal flags -> sizes -> emit (+ the 256-bin histogram Huffman needs).
+//
+// DECODE. Token boundaries depend on all previous tokens. Per 1 KiB tile the map "entry offset
+// -> exit offset" is built for every possible entry (a token overhangs by at most 128 bytes)
+// by pointer doubling in shared memory; one thread per block chains the tiles; tiles then mark
+// their true token starts the same way, count, and expand with a binary search per output byte.
+#include "bra_common.cuh"
+#include "bra_kernels.h"
+
+#include <limits.h>
+
+namespace bra {
+
+#define RL_TILE 4096
+#define RL_THREADS 256
+#define RL_INF 0x7FFFFFFF
+
+// ---- shared per-tile machinery ------------------------------------------------------------------
+struct RleTile
+{
+    uint8_t  x[16];
+    int      s[16];  // start of the maximal run containing the byte
+    int      e[16];  // end (exclusive) of that run
+    uint32_t m;      // valid bytes of this thread
+    int      j0;     // block-relative index of x[0]
+};
+
+// reduce tile summaries of other tiles: max over tiles < t of a[], min over tiles > t of c[]
+__device__ __forceinline__ void rle_carries(const int* __restrict__ last_arr, const int* __restrict__ first_arr, uint32_t t, uint32_t ntiles,
+                                            int none_before, int none_after, int* red, int& before, int& after)
+{
+    int mx = none_before, mn = none_after;
+    for (uint32_t i = threadIdx.x; i < ntiles; i += RL_THREADS)
+    {
+        if (i < t) mx = max(mx, last_arr[i]);
+        if (i > t) mn = min(mn, first_arr[i]);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        mx = max(mx, __shfl_xor_sync(BRA_FULL, mx, d));
+        mn = min(mn, __shfl_xor_sync(BRA_FULL, mn, d));
+    }
+    __syncthreads();
+    if (lane_id() == 0)
+    {
+        red[warp_id()]     = mx;
+        red[8 + warp_id()] = mn;
+    }
+    __syncthreads();
+    before = red[0];
+    after  = red[8];
+    for (int i = 1; i < 8; ++i)
+    {
+        before = max(before, red[i]);
+        after  = min(after, red[8 + i]);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void rle_load(RleTile& T, const uint8_t* __restrict__ xb, uint32_t n, uint32_t tile0, uint32_t& headmask)
+{
+    T.j0 = (int) (tile0 + threadIdx.x * 16);
+    T.m  = (uint32_t) T.j0 < n ? min(16u, n - T.j0) : 0u;
+    uint8_t prev = 0;
+    if (T.m == 16)
+    {
+        const uint4 v = *reinterpret_cast<const uint4*>(xb + T.j0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) T.x[i] = (w[i >> 2] >> ((i & 3) * 8)) & 0xFFu;
+    }
+    else
+    {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) T.x[i] = (uint32_t) i < T.m ? xb[T.j0 + i] : 0;
+    }
+    if (T.m && T.j0 > 0) prev = xb[T.j0 - 1];
+    headmask = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+    {
+        if ((uint32_t) i < T.m && ((T.j0 + i) == 0 || T.x[i] != prev)) headmask |= 1u << i;
+        prev = T.x[i];
+    }
+}
+
+// fill s[], e[] given the carries (last head before the tile, first head after the tile or n)
+__device__ __forceinline__ void rle_runs(RleTile& T, uint32_t headmask, int head_before, int head_after, int* red)
+{
+    int mylast = -1, myfirst = RL_INF;
+    if (headmask)
+    {
+        mylast  = T.j0 + (31 - __clz(headmask));
+        myfirst = T.j0 + (__ffs(headmask) - 1);
+    }
+    int run_s = max(block_excl_max(mylast, -1, red), head_before);
+    int nxt   = min(block_excl_min_rev(myfirst, RL_INF, red), head_after);
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+    {
+        if (headmask & (1u << i)) run_s = T.j0 + i;
+        T.s[i] = run_s;
+    }
+#pragma unroll
+    for (int i = 15; i >= 0; --i)
+    {
+        T.e[i] = nxt;
+        if (headmask & (1u << i)) nxt = T.j0 + i;
+    }
+}
+
+__device__ __forceinline__ uint32_t rle_litmask(const RleTile& T)
+{
+    uint32_t lit = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+    {
+        if ((uint32_t) i >= T.m) break;
+        const int L = T.e[i] - T.s[i], k = T.j0 + i - T.s[i], rho = L & 127;
+        if (L < 3 || ((rho == 1 || rho == 2) && k >= L - rho)) lit |= 1u << i;
+    }
+    return lit;
+}
+
+// ---- pass 1: run heads per tile ------------------------------------------------------------------
+__global__ void __launch_bounds__(RL_THREADS)
+    rle_enc_heads_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len, uint32_t tiles,
+                         int* __restrict__ t_first_head, int* __restrict__ t_last_head)
+{
+    __shared__ int red[16];
+    const uint32_t b = blockIdx.y, t = blockIdx.x;
+    const uint32_t n = len[b];
+    const uint32_t tile0 = t * RL_TILE;
+    if (tile0 >= n) return;
+    RleTile  T;
+    uint32_t hm;
+    rle_load(T, in + (uint64_t) b * stride, n, tile0, hm);
+    int mx = hm ? T.j0 + (31 - __clz(hm)) : -1;
+    int mn = hm ? T.j0 + (__ffs(hm) - 1) : RL_INF;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        mx = max(mx, __shfl_xor_sync(BRA_FULL, mx, d));
+        mn = min(mn, __shfl_xor_sync(BRA_FULL, mn, d));
+    }
+    if (lane_id() == 0)
+    {
+        red[warp_id()]     = mx;
+        red[8 + warp_id()] = mn;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int i = 1; i < 8; ++i)
+        {
+            mx = max(mx, red[i]);
+            mn = min(mn, red[8 + i]);
+        }
+        t_last_head[(uint64_t) b * tiles + t]  = mx;
+        t_first_head[(uint64_t) b * tiles + t] = mn;
+    }
+}
+
+// ---- pass 2: literal flags -> first/last non-literal byte per tile ---------------------------------
+__global__ void __launch_bounds__(RL_THREADS)
+    rle_enc_lit_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len, uint32_t tiles,
+                       const int* __restrict__ t_first_head, const int* __restrict__ t_last_head, int* __restrict__ t_first_nl,
+                       int* __restrict__ t_last_nl)
+{
+    __shared__ int red[34];
+    const uint32_t b = blockIdx.y, t = blockIdx.x;
+    const uint32_t n = len[b];
+    const uint32_t tile0 = t * RL_TILE;
+    if (tile0 >= n) return;
+    const uint32_t ntiles = (n + RL_TILE - 1) / RL_TILE;
+    int            hb, ha;
+    rle_carries(t_last_head + (uint64_t) b * tiles, t_first_head + (uint64_t) b * tiles, t, ntiles, -1, (int) n, red, hb, ha);
+    ha = min(ha, (int) n);
+    RleTile  T;
+    uint32_t hm;
+    rle_load(T, in + (uint64_t) b * stride, n, tile0, hm);
+    rle_runs(T, hm, hb, ha, red);
+    const uint32_t lit = rle_litmask(T);
+    const uint32_t nl  = ~lit & (T.m == 16 ? 0xFFFFu : ((1u << T.m) - 1u));
+    int mx = nl ? T.j0 + (31 - __clz(nl)) : -1;
+    int mn = nl ? T.j0 + (__ffs(nl) - 1) : RL_INF;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        mx = max(mx, __shfl_xor_sync(BRA_FULL, mx, d));
+        mn = min(mn, __shfl_xor_sync(BRA_FULL, mn, d));
+    }
+    __syncthreads();
+    if (lane_id() == 0)
+    {
+        red[warp_id()]     = mx;
+        red[8 + warp_id()] = mn;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int i = 1; i < 8; ++i)
+        {
+            mx = max(mx, red[i]);
+            mn = min(mn, red[8 + i]);
+        }
+        t_last_nl[(uint64_t) b * tiles + t]  = mx;
+        t_first_nl[(uint64_t) b * tiles + t] = mn;
+    }
+}
+
+// ---- passes 3 and 4: output size per tile, then emit ----------------------------------------------
+// EMIT == false: writes t_cnt. EMIT == true: needs t_cnt complete, writes bytes, r_len and histogram.
+template <bool EMIT>
+__global__ void __launch_bounds__(RL_THREADS)
+    rle_enc_out_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len, uint32_t tiles,
+                       const int* __restrict__ t_first_head, const int* __restrict__ t_last_head, const int* __restrict__ t_first_nl,
+                       const int* __restrict__ t_last_nl, uint32_t* __restrict__ t_cnt, uint8_t* __restrict__ out, uint64_t out_stride,
+                       uint32_t* __restrict__ r_len, uint32_t* __restrict__ hist)
+{
+    __shared__ int      red[34];
+    __shared__ uint32_t ured[34];
+    __shared__ uint8_t  stage[EMIT ? RL_TILE + 64 : 4];
+    __shared__ uint32_t shist[EMIT ? 256 : 1];
+    const uint32_t b = blockIdx.y, t = blockIdx.x;
+    const uint32_t n = len[b];
+    const uint32_t tile0 = t * RL_TILE;
+    if (tile0 >= n) return;
+    const uint32_t ntiles = (n + RL_TILE - 1) / RL_TILE;
+    int            hb, ha, nlb, nla;
+    rle_carries(t_last_head + (uint64_t) b * tiles, t_first_head + (uint64_t) b * tiles, t, ntiles, -1, (int) n, red, hb, ha);
+    rle_carries(t_last_nl + (uint64_t) b * tiles, t_first_nl + (uint64_t) b * tiles, t, ntiles, -1, (int) n, red, nlb, nla);
+    ha  = min(ha, (int) n);
+    nla = min(nla, (int) n);
+    RleTile  T;
+    uint32_t hm;
+    rle_load(T, in + (uint64_t) b * stride, n, tile0, hm);
+    rle_runs(T, hm, hb, ha, red);
+    const uint32_t lit   = rle_litmask(T);
+    const uint32_t valid = T.m == 16 ? 0xFFFFu : ((1u << T.m) - 1u);
+    const uint32_t nl    = ~lit & valid;
+
+    // stretch start (last non-literal before the byte, +1) and stretch end (first non-literal after it)
+    int mylast = nl ? T.j0 + (31 - __clz(nl)) : -1;
+    int myfirst = nl ? T.j0 + (__ffs(nl) - 1) : RL_INF;
+    int last_nl = max(block_excl_max(mylast, -1, red), nlb);
+    int next_nl = min(block_excl_min_rev(myfirst, RL_INF, red), nla);
+    int ss[16], se[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+    {
+        if (nl & (1u << i)) last_nl = T.j0 + i;
+        ss[i] = last_nl + 1;
+    }
+#pragma unroll
+    for (int i = 15; i >= 0; --i)
+    {
+        se[i] = next_nl;
+        if (nl & (1u << i)) next_nl = T.j0 + i;
+    }
+
+    uint32_t contrib[16], mysum = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+    {
+        uint32_t c = 0;
+        if ((uint32_t) i < T.m)
+        {
+            if (lit & (1u << i))
+                c = 1u + (((T.j0 + i - ss[i]) & 127) == 0);
+            else
+                c = (((T.j0 + i - T.s[i]) & 127) == 0) ? 2u : 0u;
+        }
+        contrib[i] = c;
+        mysum += c;
+    }
+    uint32_t tile_total;
+    uint32_t off = block_excl_add(mysum, ured, &tile_total);
+    if (!EMIT)
+    {
+        if (threadIdx.x == 0) t_cnt[(uint64_t) b * tiles + t] = tile_total;
+        return;
+    }
+    else
+    {
+        // output offset of the tile = sum of the counts of the tiles before it
+        uint32_t before = 0;
+        for (uint32_t i = threadIdx.x; i < t; i += RL_THREADS) before += t_cnt[(uint64_t) b * tiles + i];
+        uint32_t tile_out0;
+        block_excl_add(before, ured, &tile_out0);
+        shist[threadIdx.x]       = 0;
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+        {
+            if ((uint32_t) i >= T.m) break;
+            if (lit & (1u << i))
+            {
+                const int ks = T.j0 + i - ss[i];
+                if ((ks & 127) == 0)
+                {
+                    stage[off]     = (uint8_t) (min(128, se[i] - ss[i] - ks) - 1);
+                    stage[off + 1] = T.x[i];
+                }
+                else
+                    stage[off] = T.x[i];
+            }
+            else
+            {
+                const int k = T.j0 + i - T.s[i];
+                if ((k & 127) == 0)
+                {
+                    const int L = T.e[i] - T.s[i], rho = L & 127;
+                    const int tok = min(128, L - (rho < 3 ? rho : 0) - k);
+                    stage[off]     = (uint8_t) (1 - tok);
+                    stage[off + 1] = T.x[i];
+                }
+            }
+            off += contrib[i];
+        }
+        __syncthreads();
+        uint8_t* o = out + (uint64_t) b * out_stride + tile_out0;
+        for (uint32_t i = threadIdx.x; i < tile_total; i += RL_THREADS)
+        {
+            const uint8_t v = stage[i];
+            o[i]            = v;
+            atomicAdd(&shist[v], 1u);
+        }
+        __syncthreads();
+        if (shist[threadIdx.x]) atomicAdd(&hist[(uint64_t) b * 256 + threadIdx.x], shist[threadIdx.x]);
+        if (t + 1 == ntiles && threadIdx.x == 0) r_len[b] = tile_out0 + tile_total;
+    }
+}
+
+bool rle_encode_batch(const RleEncArgs& a, cudaStream_t st)
+{
+    if (a.nblk == 0 || a.max_n == 0) return true;
+    const uint32_t tiles = bra_div_up(a.max_n, RL_TILE);
+    const dim3     grid(tiles, a.nblk);
+    BRA_CUDA_TRY(cudaMemsetAsync(a.d_hist, 0, (size_t) a.nblk * 256 * 4, st));
+    BRA_LAUNCH(P_RLE_ENC_HEADS, st, rle_enc_heads_kernel<<<grid, RL_THREADS, 0, st>>>(a.d_in, a.stride, a.d_len, tiles, a.d_t_first_head, a.d_t_last_head));
+    BRA_LAUNCH(P_RLE_ENC_LIT, st, rle_enc_lit_kernel<<<grid, RL_THREADS, 0, st>>>(a.d_in, a.stride, a.d_len, tiles, a.d_t_first_head, a.d_t_last_head, a.d_t_first_nl,
+                                                    a.d_t_last_nl));
+    BRA_LAUNCH(P_RLE_ENC_SIZE, st, rle_enc_out_kernel<false><<<grid, RL_THREADS, 0, st>>>(a.d_in, a.stride, a.d_len, tiles, a.d_t_first_head, a.d_t_last_head,
+                                                           a.d_t_first_nl, a.d_t_last_nl, a.d_t_cnt, nullptr, 0, nullptr, nullptr));
+    BRA_LAUNCH(P_RLE_ENC_EMIT, st, rle_enc_out_kernel<true><<<grid, RL_THREADS, 0, st>>>(a.d_in, a.stride, a.d_len, tiles, a.d_t_first_head, a.d_t_last_head,
+                                                          a.d_t_first_nl, a.d_t_last_nl, a.d_t_cnt, a.d_out, a.out_stride, a.d_rlen,
+                                                          a.d_hist));
+    BRA_CUDA_TRY(cudaGetLastError());
+    return true;
+}
+
+// ================================================================================================
+// DECODE
+// ================================================================================================
+#define RD_TILE 1024
+#define RD_THREADS 256
+#define RD_ENTRIES 130  // a token starting in the previous tile can overhang by 0..129 bytes... exit offsets 0..128
+
+__device__ __forceinline__ uint32_t rle_tok_len(uint8_t c)  // bytes of input the token occupies
+{
+    const int8_t s = (int8_t) c;
+    return s >= 0 ? (uint32_t) s + 2u : (s == -128 ? 1u : 2u);
+}
+__device__ __forceinline__ uint32_t rle_tok_out(uint8_t c)  // bytes of output it produces
+{
+    const int8_t s = (int8_t) c;
+    return s >= 0 ? (uint32_t) s + 1u : (s == -128 ? 0u : (uint32_t) (1 - s));
+}
+
+// Builds J[i] = first position >= tile_n reached from i (absolute exit), in shared memory.
+__device__ __forceinline__ void rle_dec_jump_closure(const uint8_t* __restrict__ xb, uint32_t tile0, uint32_t tile_n, uint16_t* Ja, uint16_t* Jb)
+{
+    for (uint32_t i = threadIdx.x; i < RD_TILE; i += RD_THREADS)
+        Ja[i] = i < tile_n ? (uint16_t) (i + rle_tok_len(xb[tile0 + i])) : (uint16_t) i;
+    __syncthreads();
+    uint16_t *src = Ja, *dst = Jb;
+    for (int r = 0; r < 10; ++r)
+    {
+        for (uint32_t i = threadIdx.x; i < RD_TILE; i += RD_THREADS)
+        {
+            const uint16_t j = src[i];
+            dst[i]           = j < tile_n ? src[j] : j;
+        }
+        __syncthreads();
+        uint16_t* tmp = src;
+        src           = dst;
+        dst           = tmp;
+    }
+    // 10 swaps: result is back in Ja
+}
+
+__global__ void __launch_bounds__(RD_THREADS)
+    rle_dec_exit_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ rlen, uint32_t tiles,
+                        uint8_t* __restrict__ t_exit /* [b][tile][RD_ENTRIES] */)
+{
+    __shared__ uint16_t Ja[RD_TILE], Jb[RD_TILE];
+    const uint32_t      b = blockIdx.y, t = blockIdx.x;
+    const uint32_t      r = rlen[b];
+    const uint32_t      tile0 = t * RD_TILE;
+    if (tile0 >= r) return;
+    const uint32_t tile_n = min((uint32_t) RD_TILE, r - tile0);
+    rle_dec_jump_closure(in + (uint64_t) b * stride, tile0, tile_n, Ja, Jb);
+    if (threadIdx.x < RD_ENTRIES)
+    {
+        // entries beyond the tile (only possible in a short last tile) are never followed
+        const uint32_t e = threadIdx.x;
+        const uint32_t x = e < tile_n ? (uint32_t) Ja[e] - tile_n : 0u;
+        t_exit[((uint64_t) b * tiles + t) * RD_ENTRIES + e] = (uint8_t) min(x, 255u);
+    }
+}
+
+__global__ void rle_dec_chain_kernel(const uint32_t* __restrict__ rlen, uint32_t tiles, const uint8_t* __restrict__ t_exit,
+                                     uint8_t* __restrict__ t_entry, uint32_t nblk)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk) return;
+    const uint32_t r      = rlen[b];
+    const uint32_t ntiles = (r + RD_TILE - 1) / RD_TILE;
+    uint32_t       e      = 0;
+    for (uint32_t t = 0; t < ntiles; ++t)
+    {
+        t_entry[(uint64_t) b * tiles + t] = (uint8_t) e;
+        e = t_exit[((uint64_t) b * tiles + t) * RD_ENTRIES + e];
+    }
+}
+
+__global__ void __launch_bounds__(RD_THREADS)
+    rle_dec_mark_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ rlen, uint32_t tiles,
+                        const uint8_t* __restrict__ t_entry, uint32_t* __restrict__ t_tok /* [b][tile][32] */, uint32_t* __restrict__ t_ocnt,
+                        uint32_t* __restrict__ err)
+{
+    __shared__ uint16_t Ja[RD_TILE], Jb[RD_TILE];
+    __shared__ uint8_t  reach[RD_TILE];
+    __shared__ uint32_t ured[34];
+    const uint32_t      b = blockIdx.y, t = blockIdx.x;
+    const uint32_t      r = rlen[b];
+    const uint32_t      tile0 = t * RD_TILE;
+    if (tile0 >= r) return;
+    const uint32_t tile_n = min((uint32_t) RD_TILE, r - tile0);
+    const uint8_t* xb     = in + (uint64_t) b * stride;
+    const uint32_t entry  = t_entry[(uint64_t) b * tiles + t];
+
+    for (uint32_t i = threadIdx.x; i < RD_TILE; i += RD_THREADS)
+    {
+        Ja[i]    = i < tile_n ? (uint16_t) (i + rle_tok_len(xb[tile0 + i])) : (uint16_t) i;
+        reach[i] = (i == entry && i < tile_n);
+    }
+    __syncthreads();
+    uint16_t *src = Ja, *dst = Jb;
+    for (int rd = 0; rd < 10; ++rd)
+    {
+        for (uint32_t i = threadIdx.x; i < RD_TILE; i += RD_THREADS)
+        {
+            const uint16_t j = src[i];
+            if (reach[i] && j < tile_n) reach[j] = 1;  // J^(2^rd) of a reachable start is reachable
+            dst[i] = j < tile_n ? src[j] : j;
+        }
+        __syncthreads();
+        uint16_t* tmp = src;
+        src           = dst;
+        dst           = tmp;
+    }
+    // token bitmap + output count; truncated tokens are the reference's error exits (bra_rle.c:136,148)
+    uint32_t mycnt = 0;
+    bool     bad   = false;
+    for (uint32_t k = 0; k < RD_TILE / RD_THREADS; ++k)
+    {
+        const uint32_t i    = k * RD_THREADS + threadIdx.x;
+        const bool     tok  = i < tile_n && reach[i];
+        const uint32_t ball = __ballot_sync(BRA_FULL, tok);
+        if (lane_id() == 0) t_tok[((uint64_t) b * tiles + t) * 32 + (i >> 5)] = ball;
+        if (tok)
+        {
+            const uint8_t c = xb[tile0 + i];
+            mycnt += rle_tok_out(c);
+            if ((uint64_t) tile0 + i + rle_tok_len(c) > r) bad = true;
+        }
+    }
+    uint32_t total;
+    block_excl_add(mycnt, ured, &total);
+    if (threadIdx.x == 0) t_ocnt[(uint64_t) b * tiles + t] = total;
+    if (bad) err[b] = 1;
+}
+
+__global__ void __launch_bounds__(RD_THREADS)
+    rle_dec_expand_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ rlen, uint32_t tiles,
+                          const uint32_t* __restrict__ t_tok, const uint32_t* __restrict__ t_ocnt, const uint32_t* __restrict__ err,
+                          uint8_t* __restrict__ out, uint64_t out_stride, uint32_t out_cap, uint32_t* __restrict__ n_len)
+{
+    __shared__ uint32_t tstart[RD_TILE / 1 + 1];  // output start of each token of the tile (compacted)
+    __shared__ uint16_t tsrc[RD_TILE];            // input position (tile-relative) of each token
+    __shared__ uint32_t ured[34];
+    const uint32_t      b = blockIdx.y, t = blockIdx.x;
+    const uint32_t      r = rlen[b];
+    const uint32_t      tile0 = t * RD_TILE;
+    if (tile0 >= r) return;
+    const uint32_t ntiles = (r + RD_TILE - 1) / RD_TILE;
+    const uint8_t* xb     = in + (uint64_t) b * stride;
+
+    // offset of this tile's output; the last tile also publishes the decoded size (0 on error)
+    uint32_t before = 0;
+    for (uint32_t i = threadIdx.x; i < t; i += RD_THREADS) before += t_ocnt[(uint64_t) b * tiles + i];
+    uint32_t out0;
+    block_excl_add(before, ured, &out0);
+    const uint32_t mine  = t_ocnt[(uint64_t) b * tiles + t];
+    const bool     isbad = err[b] != 0 || (uint64_t) out0 + mine > out_cap;
+    if (t + 1 == ntiles && threadIdx.x == 0) n_len[b] = isbad ? 0u : out0 + mine;
+    if (isbad || out == nullptr) return;  // out == nullptr: size query only (bra_rle_decode_compute_size)
+
+    // compact the tokens: 4 consecutive positions per thread
+    const uint32_t i0   = threadIdx.x * 4;
+    const uint32_t bits = (t_tok[((uint64_t) b * tiles + t) * 32 + (i0 >> 5)] >> (i0 & 31)) & 0xFu;
+    uint32_t       olen[4], nt = 0, osum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        olen[k] = 0;
+        if (bits & (1u << k))
+        {
+            olen[k] = rle_tok_out(xb[tile0 + i0 + k]);
+            ++nt;
+            osum += olen[k];
+        }
+    }
+    uint32_t ntok, dummy;
+    uint32_t ti = block_excl_add(nt, ured, &ntok);
+    uint32_t oo = block_excl_add(osum, ured, &dummy);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (bits & (1u << k))
+        {
+            tstart[ti] = oo;
+            tsrc[ti]   = (uint16_t) (i0 + k);
+            ++ti;
+            oo += olen[k];
+        }
+    if (threadIdx.x == 0) tstart[ntok] = mine;
+    __syncthreads();
+
+    uint8_t* ob = out + (uint64_t) b * out_stride + out0;
+    for (uint32_t o = threadIdx.x; o < mine; o += RD_THREADS)
+    {
+        uint32_t lo = 0, hi = ntok;  // last token with tstart <= o
+        while (hi - lo > 1)
+        {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (tstart[mid] <= o)
+                lo = mid;
+            else
+                hi = mid;
+        }
+        const uint32_t src = tile0 + tsrc[lo];
+        const int8_t   c   = (int8_t) xb[src];
+        ob[o]              = c >= 0 ? xb[src + 1 + (o - tstart[lo])] : xb[src + 1];
+    }
+}
+
+bool rle_decode_batch(const RleDecArgs& a, cudaStream_t st)
+{
+    if (a.nblk == 0 || a.max_r == 0) return true;
+    const uint32_t tiles = bra_div_up(a.max_r, RD_TILE);
+    const dim3     grid(tiles, a.nblk);
+    BRA_LAUNCH(P_RLE_DEC_EXIT, st, rle_dec_exit_kernel<<<grid, RD_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_exit));
+    BRA_LAUNCH(P_RLE_DEC_CHAIN, st, rle_dec_chain_kernel<<<bra_div_up(a.nblk, 32), 32, 0, st>>>(a.d_rlen, tiles, a.d_t_exit, a.d_t_entry, a.nblk));
+    BRA_LAUNCH(P_RLE_DEC_MARK, st, rle_dec_mark_kernel<<<grid, RD_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_entry, a.d_t_tok, a.d_t_ocnt, a.d_err));
+    if (a.size_only)
+        BRA_LAUNCH(P_RLE_DEC_EXPAND, st, rle_dec_expand_kernel<<<grid, RD_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_tok, a.d_t_ocnt, a.d_err, nullptr, 0, 0xFFFFFFFFu,
+                                                           a.d_nlen));
+    else
+        BRA_LAUNCH(P_RLE_DEC_EXPAND, st, rle_dec_expand_kernel<<<grid, RD_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_tok, a.d_t_ocnt, a.d_err, a.d_out,
+                                                           a.out_stride, a.out_cap, a.d_nlen));
+    BRA_CUDA_TRY(cudaGetLastError());
+    return true;
+}
+
+uint32_t rle_enc_tiles(uint32_t max_n) { return bra_div_up(max_n, RL_TILE); }
+uint32_t rle_dec_tiles(uint32_t max_r) { return bra_div_up(max_r, RD_TILE); }
+uint32_t rle_dec_entries() { return RD_ENTRIES; }
+
+}  // namespace bra

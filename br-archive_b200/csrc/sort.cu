@@ -1,0 +1,233 @@
+// sort.cu -- batched, segmented, stable LSD radix-sort pass (8-bit digit).
+//
+// Used three ways on the hot path:
+//   * forward BWT: initial sort of rotation indices by their first 4 bytes (4 passes) and the
+//     per-doubling-round stable re-bucketing by rank (2-3 passes)  -- replaces the qsort_r call
+//     of reference src/encoders/bra_bwt.c:91;
+//   * inverse BWT: one pass with the BWT bytes as keys builds `transform[]`, i.e. the stable
+//     counting sort of reference bra_bwt.c:142-159.
+//
+// One pass = three kernels over every block of the batch (blocks never mix):
+//   hist    : per 4096-element tile, shared-memory 256-bin histogram  -> hist[b][digit][tile]
+//   scan    : per block, exclusive scan in (digit, tile) order        -> global offsets
+//   scatter : per tile, stable in-tile ranking with warp match/ballot, shared-memory reorder so
+//             that each digit's run leaves the SM as one contiguous store, then the scatter.
+// Algorithmic traffic per pass and element: read key+value, write key+value (+ key re-read by
+// hist). HBM/L2 bound; no tensor-core work.
+#include "bra_common.cuh"
+#include "bra_kernels.h"
+
+namespace bra {
+
+#define RS_TILE 4096
+#define RS_THREADS 256
+#define RS_ITEMS 16  // per thread
+
+template <typename KeyT>
+__device__ __forceinline__ uint32_t rs_digit(KeyT k, uint32_t shift)
+{
+    return ((uint32_t) k >> shift) & 0xFFu;
+}
+
+// ------------------------------------------------------------------------------------ hist
+template <typename KeyT>
+__global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restrict__ keys, uint64_t stride, const uint32_t* __restrict__ len,
+                                                             const uint8_t* __restrict__ skip, uint32_t shift, uint32_t tiles,
+                                                             uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t h[256];
+    const uint32_t      b = blockIdx.y, t = blockIdx.x;
+    if (skip && skip[b]) return;
+    const uint32_t n     = len[b];
+    const uint32_t tile0 = t * RS_TILE;
+    uint32_t*      out   = hist + ((uint64_t) b * 256) * tiles + t;  // [b][digit][tile]
+    if (tile0 >= n)
+    {
+        out[(uint64_t) threadIdx.x * tiles] = 0;
+        return;
+    }
+    h[threadIdx.x] = 0;
+    __syncthreads();
+    const KeyT*    k  = keys + (uint64_t) b * stride + tile0;
+    const uint32_t tn = min((uint32_t) RS_TILE, n - tile0);
+    for (uint32_t i = threadIdx.x; i < tn; i += RS_THREADS) atomicAdd(&h[rs_digit(k[i], shift)], 1u);
+    __syncthreads();
+    out[(uint64_t) threadIdx.x * tiles] = h[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------ scan
+// One CTA per block: exclusive scan of 256*tiles counters in place.
+__global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t* __restrict__ hist, const uint8_t* __restrict__ skip, uint32_t tiles)
+{
+    __shared__ uint32_t red[33];
+    const uint32_t      b = blockIdx.x;
+    if (skip && skip[b]) return;
+    uint32_t*      h     = hist + ((uint64_t) b * 256) * tiles;
+    const uint32_t total = 256u * tiles;
+    uint32_t       carry = 0;
+    for (uint32_t base = 0; base < total; base += 1024 * 4)
+    {
+        // 4 consecutive counters per thread
+        const uint32_t i0 = base + threadIdx.x * 4;
+        uint32_t       v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (i0 + j < total) ? h[i0 + j] : 0u;
+        const uint32_t s = v[0] + v[1] + v[2] + v[3];
+        uint32_t       tot;
+        uint32_t       ex = block_excl_add(s, red, &tot) + carry;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            if (i0 + j < total) h[i0 + j] = ex;
+            ex += v[j];
+        }
+        carry += tot;
+        __syncthreads();
+    }
+}
+
+// --------------------------------------------------------------------------------- scatter
+// OUT_MODE 0: write keys_out and vals_out; 1: write vals_out only;
+//          2: write packed (val << 8) | key8 into vals_out (inverse-BWT "next row | byte" word)
+template <typename KeyT, bool IMPLICIT_VALS, int OUT_MODE>
+__global__ void __launch_bounds__(RS_THREADS)
+    rs_scatter_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, KeyT* __restrict__ keys_out,
+                      uint32_t* __restrict__ vals_out, uint64_t stride, const uint32_t* __restrict__ len,
+                      const uint8_t* __restrict__ skip, uint32_t shift, uint32_t tiles, const uint32_t* __restrict__ hist)
+{
+    __shared__ uint32_t wcnt[8][256];     // per-warp digit counters -> per-warp bases
+    __shared__ uint32_t dstart[256];      // start of each digit's run inside the sorted tile
+    __shared__ uint32_t goff[256];        // global destination of each digit's run for this tile
+    __shared__ KeyT     skey[RS_TILE];
+    __shared__ uint32_t sval[RS_TILE];
+    __shared__ uint32_t red[33];
+
+    const uint32_t b = blockIdx.y, t = blockIdx.x;
+    if (skip && skip[b]) return;
+    const uint32_t n     = len[b];
+    const uint32_t tile0 = t * RS_TILE;
+    if (tile0 >= n) return;
+    const uint32_t tn   = min((uint32_t) RS_TILE, n - tile0);
+    const uint64_t base = (uint64_t) b * stride;
+    const uint32_t w = warp_id(), l = lane_id();
+
+    for (int i = threadIdx.x; i < 8 * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+    __syncthreads();
+
+    // warp w owns elements [w*512, w*512+512) of the tile, visited in 16 rounds of 32 (memory order)
+    KeyT     k[RS_ITEMS];
+    uint32_t v[RS_ITEMS];
+    uint32_t rk[RS_ITEMS];  // rank among equal digits inside the warp
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+    {
+        const uint32_t e = w * 512 + r * 32 + l;
+        const bool     ok = e < tn;
+        k[r] = ok ? keys[base + tile0 + e] : (KeyT) 0;
+        v[r] = IMPLICIT_VALS ? (tile0 + e) : (ok ? vals[base + tile0 + e] : 0u);
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+    {
+        const uint32_t e  = w * 512 + r * 32 + l;
+        const bool     ok = e < tn;
+        const uint32_t d  = ok ? rs_digit(k[r], shift) : 256u;  // 256 = padding, matches only padding
+        const uint32_t peers = __match_any_sync(BRA_FULL, d);
+        const uint32_t before = __popc(peers & lanemask_lt());
+        const int      leader = __ffs(peers) - 1;
+        uint32_t       old    = 0;
+        if (ok && (int) l == leader)
+        {
+            old        = wcnt[w][d];
+            wcnt[w][d] = old + __popc(peers);
+        }
+        old   = __shfl_sync(BRA_FULL, old, leader);
+        rk[r] = old + before;
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // per digit: exclusive scan over warps; digit totals -> exclusive scan over digits
+    {
+        const uint32_t d = threadIdx.x;
+        uint32_t       run = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+        {
+            const uint32_t c = wcnt[i][d];
+            wcnt[i][d]       = run;
+            run += c;
+        }
+        const uint32_t ex = block_excl_add(run, red, nullptr);
+        dstart[d]         = ex;
+        goff[d]           = hist[((uint64_t) b * 256 + d) * tiles + t];
+    }
+    __syncthreads();
+
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+    {
+        const uint32_t e = w * 512 + r * 32 + l;
+        if (e < tn)
+        {
+            const uint32_t d   = rs_digit(k[r], shift);
+            const uint32_t pos = dstart[d] + wcnt[w][d] + rk[r];
+            skey[pos]          = k[r];
+            sval[pos]          = v[r];
+        }
+    }
+    __syncthreads();
+
+    for (uint32_t e = threadIdx.x; e < tn; e += RS_THREADS)
+    {
+        const KeyT     kk  = skey[e];
+        const uint32_t d   = rs_digit(kk, shift);
+        const uint64_t dst = base + goff[d] + (e - dstart[d]);
+        if (OUT_MODE == 0)
+        {
+            keys_out[dst] = kk;
+            vals_out[dst] = sval[e];
+        }
+        else if (OUT_MODE == 1)
+            vals_out[dst] = sval[e];
+        else
+            vals_out[dst] = (sval[e] << 8) | (uint32_t) kk;
+    }
+}
+
+template <typename KeyT, bool IMPLICIT, int OUT_MODE>
+static bool radix_pass_t(const KeyT* keys, const uint32_t* vals, KeyT* keys_out, uint32_t* vals_out, uint64_t stride, const uint32_t* d_len,
+                         const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t* d_hist, cudaStream_t st)
+{
+    if (nblk == 0 || max_len == 0) return true;
+    const uint32_t tiles = bra_div_up(max_len, RS_TILE);
+    BRA_LAUNCH(P_RS_HIST, st, rs_hist_kernel<KeyT><<<dim3(tiles, nblk), RS_THREADS, 0, st>>>(keys, stride, d_len, d_skip, shift, tiles, d_hist));
+    BRA_LAUNCH(P_RS_SCAN, st, rs_scan_kernel<<<nblk, 1024, 0, st>>>(d_hist, d_skip, tiles));
+    BRA_LAUNCH(P_RS_SCATTER, st, rs_scatter_kernel<KeyT, IMPLICIT, OUT_MODE>
+        <<<dim3(tiles, nblk), RS_THREADS, 0, st>>>(keys, vals, keys_out, vals_out, stride, d_len, d_skip, shift, tiles, d_hist));
+    BRA_CUDA_TRY(cudaGetLastError());
+    return true;
+}
+
+size_t radix_hist_bytes(uint32_t max_len, uint32_t nblk) { return (size_t) nblk * 256 * bra_div_up(max_len, RS_TILE) * sizeof(uint32_t); }
+
+bool radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t stride,
+                    const uint32_t* d_len, const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t* d_hist,
+                    cudaStream_t st)
+{
+    return radix_pass_t<uint32_t, false, 0>(keys, vals, keys_out, vals_out, stride, d_len, d_skip, max_len, nblk, shift, d_hist, st);
+}
+
+bool radix_pass_u8_index_packed(const uint8_t* keys, uint32_t* packed_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len,
+                                uint32_t nblk, uint32_t* d_hist, cudaStream_t st)
+{
+    return radix_pass_t<uint8_t, true, 2>(keys, nullptr, nullptr, packed_out, stride, d_len, nullptr, max_len, nblk, 0, d_hist, st);
+}
+
+bool radix_pass_u8_index(const uint8_t* keys, uint32_t* vals_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len, uint32_t nblk,
+                         uint32_t* d_hist, cudaStream_t st)
+{
+    return radix_pass_t<uint8_t, true, 1>(keys, nullptr, nullptr, vals_out, stride, d_len, nullptr, max_len, nblk, 0, d_hist, st);
+}
+
+}  // namespace bra

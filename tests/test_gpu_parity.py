@@ -1,0 +1,343 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle and the committed
+reference outputs. Bit-exact everywhere (byte/integer work: there is no tolerance).
+
+Layout of this file follows the reference's own test/test_bra_encoders.cpp and
+test/test_bra_crc32c.cpp: per-stage known answers first, composed round trips after, then the
+batched entry points at the BASELINE block sizes.
+"""
+import random
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+H = bytes.fromhex
+
+
+def _first_diff(a, b):
+    if a is None or b is None:
+        return f"got None: {a is None} expected None: {b is None}"
+    if len(a) != len(b):
+        return f"length {len(a)} != {len(b)}"
+    x = np.frombuffer(a, dtype=np.uint8)
+    y = np.frombuffer(b, dtype=np.uint8)
+    d = np.nonzero(x != y)[0]
+    return "equal" if d.size == 0 else f"{d.size} bytes differ, first at {int(d[0])}: {x[d[0]]} != {y[d[0]]}"
+
+
+def _runs(rng, n, alphabet=3, lens=(1, 1, 1, 2, 2, 3, 4, 5, 126, 127, 128, 129, 130, 131, 255, 256, 257, 258, 259, 300, 390, 5000)):
+    out = bytearray()
+    while len(out) < n:
+        out += bytes([rng.randrange(alphabet)]) * rng.choice(lens)
+    return bytes(out[:n])
+
+
+def _text(pkg, vocab, n, seed=1):
+    return pkg.gen_text(n, vocab, seed).tobytes()
+
+
+# ------------------------------------------------------------------------------------------ CRC32C
+def test_crc32c_known_answers(dropin, golden, oracle):
+    for v in golden["unit_tests"]["crc32c"]:
+        for impl in ("bra_crc32c", "bra_crc32c_table", "bra_crc32c_sse42"):
+            assert dropin.crc32c(H(v["in"]), impl=impl) == v["crc"]
+    d = b"123456789"
+    assert dropin.crc32c(d[5:], dropin.crc32c(d[:5])) == 0xE3069283
+    assert dropin.crc32c(b"") == 0 and dropin.crc32c(b"", 0x1234) == 0x1234
+    d = b"Hello World!"
+    assert dropin.crc32c_combine(dropin.crc32c(d[:6]), dropin.crc32c(d[6:]), 6) == 0xFE6CF1DC
+    fox = b"The quick brown fox jumps over the lazy dog"
+    for i in range(1, len(fox) + 1):  # every prefix, like test_bra_crc32c_consistency
+        assert dropin.crc32c(fox[:i], impl="bra_crc32c_table") == dropin.crc32c(fox[:i], impl="bra_crc32c_sse42") == oracle.crc32c(fox[:i])
+
+
+def test_crc32c_sizes(dropin, oracle):
+    rng = np.random.default_rng(1)
+    for n in (1, 2, 63, 64, 65, 127, 4095, 16383, 16384, 16385, 16384 * 3 + 77, 1 << 20, (1 << 20) + 13, 5_000_001):
+        d = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        prev = int(rng.integers(0, 1 << 32))
+        assert dropin.crc32c(d) == oracle.crc32c(d), n
+        assert dropin.crc32c(d, prev) == oracle.crc32c(d, prev), n
+
+
+# ------------------------------------------------------------------------------------------ BWT
+def test_bwt_known_answers(dropin, golden):
+    for v in golden["unit_tests"]["bwt"]:
+        assert dropin.bwt_encode(H(v["in"])) == (H(v["out"]), v["primary"])
+        assert dropin.bwt_decode(H(v["out"]), v["primary"]) == H(v["in"])
+
+
+def test_bwt_golden_blocks(dropin, golden):
+    for name, b in golden["blocks"].items():
+        l, pi = dropin.bwt_encode2(H(b["in"]))
+        assert pi == b["primary"], (name, pi, b["primary"])
+        assert l == H(b["bwt"]), (name, _first_diff(l, H(b["bwt"])))
+        assert dropin.bwt_decode2(H(b["bwt"]), b["primary"]) == H(b["in"]), name
+
+
+def test_bwt_shapes_vs_oracle(dropin, oracle, pkg, vocab):
+    rng = random.Random(2)
+    nrng = np.random.default_rng(2)
+    cases = []
+    for n in (1, 2, 3, 4, 5, 7, 16, 17, 255, 256, 4095, 4096, 4097, 8191, 70001):
+        cases.append(nrng.integers(0, 256, n, dtype=np.uint8).tobytes())
+        cases.append(nrng.integers(0, 2, n, dtype=np.uint8).tobytes())
+    cases.append(_text(pkg, vocab, 300_000))
+    cases.append(_runs(rng, 100_000))
+    cases.append(b"0123456789abcdef" * 8192)          # exactly periodic, period divides n (C4a)
+    cases.append((bytes(nrng.integers(0, 256, 251, dtype=np.uint8)) * 600)[:131072])  # long repeat, not cyclic (C4b)
+    cases.append(b"ab" * 5000 + b"c")
+    cases.append(bytes(40000))
+    cases.append(b"abc" * 4096 * 3)
+    for d in cases:
+        exp = oracle.bwt_encode(d)
+        got = dropin.bwt_encode2(d)
+        assert got[1] == exp[1], (len(d), got[1], exp[1])
+        assert got[0] == exp[0], (len(d), _first_diff(got[0], exp[0]))
+        back = dropin.bwt_decode2(exp[0], exp[1])
+        assert back == d, (len(d), _first_diff(back, d))
+
+
+# ------------------------------------------------------------------------------------------ MTF
+def test_mtf_known_answers(dropin, golden):
+    for v in golden["unit_tests"]["mtf"]:
+        assert dropin.mtf_encode(H(v["in"])) == H(v["out"])
+        assert dropin.mtf_decode(H(v["out"])) == H(v["in"])
+
+
+def test_mtf_shapes_vs_oracle(dropin, oracle):
+    nrng = np.random.default_rng(3)
+    for n in (1, 2, 127, 128, 129, 4095, 4096, 4097, 8192, 12289, 100_003, 1 << 20):
+        for hi in (256, 4, 1):
+            d = nrng.integers(0, hi, n, dtype=np.uint8).tobytes()
+            e = dropin.mtf_encode(d)
+            assert e == oracle.mtf_encode(d), (n, hi, _first_diff(e, oracle.mtf_encode(d)))
+            back = dropin.mtf_decode(e)
+            assert back == d, (n, hi, _first_diff(back, d))
+            r = nrng.integers(0, hi, n, dtype=np.uint8).tobytes()  # arbitrary ranks decode the same way
+            assert dropin.mtf_decode(r) == oracle.mtf_decode(r), (n, hi)
+
+
+# ------------------------------------------------------------------------------------------ RLE
+def test_rle_known_answers(dropin, golden):
+    for v in golden["unit_tests"]["rle"]:
+        assert dropin.rle_encode(H(v["in"])) == H(v["out"])
+        assert dropin.rle_decode(H(v["out"])) == H(v["in"])
+        assert dropin.rle_decode_size(H(v["out"])) == len(H(v["in"]))
+
+
+def test_rle_shapes_vs_oracle(dropin, oracle):
+    rng = random.Random(4)
+    nrng = np.random.default_rng(4)
+    cases = [bytes([7]) * n for n in (1, 2, 3, 127, 128, 129, 130, 131, 4095, 4096, 4097, 4099, 100_000)]
+    cases += [nrng.integers(0, 256, n, dtype=np.uint8).tobytes() for n in (1, 2, 3, 129, 4096, 4097, 50_000, 1 << 20)]
+    cases += [_runs(rng, n) for n in (10, 1000, 4096, 4097, 9000, 70_000, 300_000)]
+    cases += [bytes(5000) + b"ab" + bytes(4094) + b"x", b"ab" * 3000 + bytes(9000) + b"cd" * 100]
+    for d in cases:
+        e = dropin.rle_encode(d)
+        exp = oracle.rle_encode(d)
+        assert e == exp, (len(d), _first_diff(e, exp))
+        assert dropin.rle_decode_size(e) == len(d)
+        back = dropin.rle_decode(e)
+        assert back == d, (len(d), _first_diff(back, d))
+
+
+def test_rle_decode_errors_and_noops(dropin, oracle, capfd):
+    for bad in (b"\x05abc", b"\xfe", b"\x80", b"\x80\x80", b"\x00", b"\x00a\x80\xffb", b"\x7f" + b"a" * 127, b"\x00a" * 3000 + b"\x05ab"):
+        assert dropin.rle_decode_size(bad) == oracle.rle_decode_size(bad), bad[:8]
+        assert dropin.rle_decode(bad) == oracle.rle_decode(bad), bad[:8]
+    capfd.readouterr()
+
+
+# ------------------------------------------------------------------------------------------ Huffman
+def test_huffman_known_answers(dropin, golden, capfd):
+    for v in golden["unit_tests"]["huffman"]:
+        lengths, payload = dropin.huffman_encode(H(v["in"]))
+        assert lengths == H(v["lengths"]) and payload == H(v["payload"])
+        assert dropin.huffman_decode(lengths, payload, len(H(v["in"]))) == H(v["in"])
+    assert dropin.huffman_encode(b"") is None
+    capfd.readouterr()
+
+
+def test_huffman_shapes_vs_oracle(dropin, oracle):
+    nrng = np.random.default_rng(5)
+    cases = []
+    for n in (1, 2, 15, 16, 17, 4095, 4096, 4097, 40_000, 1 << 20):
+        cases.append(nrng.integers(0, 256, n, dtype=np.uint8).tobytes())
+        cases.append(nrng.integers(0, 2, n, dtype=np.uint8).tobytes())
+        cases.append(bytes([9]) * n)
+        k = 40
+        p = nrng.dirichlet(np.ones(k) * 0.05)
+        cases.append(nrng.choice(k, size=n, p=p).astype(np.uint8).tobytes())
+    fib = [1, 1]
+    while len(fib) < 27:
+        fib.append(fib[-1] + fib[-2])
+    deep = np.repeat(np.arange(len(fib), dtype=np.uint8), fib)
+    nrng.shuffle(deep)
+    cases.append(deep.tobytes())  # code lengths up to 26
+    for d in cases:
+        got = dropin.huffman_encode(d)
+        exp = oracle.huffman_encode(d)
+        assert got[0] == exp[0], (len(d), "lengths differ")
+        assert got[1] == exp[1], (len(d), _first_diff(got[1], exp[1]))
+        back = dropin.huffman_decode(exp[0], exp[1], len(d))
+        assert back == d, (len(d), _first_diff(back, d))
+
+
+def test_huffman_decode_corrupt_vs_oracle(dropin, oracle, capfd):
+    rng = random.Random(6)
+    lengths, payload = oracle.huffman_encode(b"BANANA" * 50)
+    agree = 0
+    for _ in range(200):
+        l = bytearray(lengths)
+        p = bytearray(payload + bytes(rng.randrange(256) for _ in range(rng.randrange(3))))
+        for _ in range(rng.randrange(2)):
+            l[rng.choice([65, 66, 78])] = rng.randrange(1, 4)
+        if rng.random() < 0.5:
+            p[rng.randrange(len(p))] ^= 1 << rng.randrange(8)
+        osz = rng.choice([300, 300, 299, 301, 100])
+        exp = oracle.huffman_decode(bytes(l), bytes(p), osz)
+        got = dropin.huffman_decode(bytes(l), bytes(p), osz)
+        kraft = sum(2.0 ** -x for x in l if x)
+        if kraft <= 1.0:  # prefix codes: identical behaviour, errors included
+            assert got == exp, (bytes(l)[64:80], osz, got is None, exp is None)
+            agree += 1
+        else:             # oversubscribed lengths: this implementation always rejects
+            assert got is None
+    assert agree > 50
+    capfd.readouterr()
+
+
+# ------------------------------------------------------------------------------------------ chains
+def test_stage_chain_golden_blocks(dropin, golden):
+    """bwt+mtf+rle+huffman through the per-stage API == the reference's stored outputs (C1)."""
+    for name, b in golden["blocks"].items():
+        hdr, payload, crc = dropin.encode_block(H(b["in"]))
+        assert crc == b["crc32c"], name
+        assert int.from_bytes(hdr[:4], "little") == b["primary"], name
+        assert hdr[4:260] == H(b["lengths"]), name
+        assert payload == H(b["payload"]), (name, _first_diff(payload, H(b["payload"])))
+        assert dropin.decode_block(hdr, payload) == H(b["in"]), name
+
+
+def _check_batch(pkg, oracle, data: bytes, block: int, max_batch: int, full_compare_blocks=None):
+    import torch
+    ctx = pkg.Context(0, block, max_batch)
+    try:
+        n = len(data)
+        nblk = (n + block - 1) // block
+        d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        hdr, pay, crc = ctx.encode_device(d_in, n)
+        torch.cuda.synchronize()
+        hdr_h = hdr.cpu().numpy().reshape(nblk, 268)
+        crc_h = crc.cpu().numpy().astype(np.uint32)
+        pay_h = pay.cpu().numpy().reshape(nblk, ctx.payload_stride)
+        which = range(nblk) if full_compare_blocks is None else full_compare_blocks
+        for b in which:
+            blk = data[b * block:(b + 1) * block]
+            eh, ep, ec = oracle.encode_block(blk)
+            c = int.from_bytes(hdr_h[b, 264:268].tobytes(), "little")
+            assert int(crc_h[b]) == ec, (b, "crc")
+            assert hdr_h[b].tobytes() == eh, (b, "header", _first_diff(hdr_h[b].tobytes(), eh))
+            assert pay_h[b, :c].tobytes() == ep, (b, _first_diff(pay_h[b, :c].tobytes(), ep))
+        out, out_len, crc2, status = ctx.decode_device(hdr, pay, nblk)
+        torch.cuda.synchronize()
+        assert int(status.abs().sum()) == 0
+        lens = out_len.cpu().numpy()
+        assert int(lens.sum()) == n
+        back = out.cpu().numpy().reshape(nblk, block)
+        for b in range(nblk):
+            blk = data[b * block:(b + 1) * block]
+            assert back[b, :lens[b]].tobytes() == blk, (b, _first_diff(back[b, :lens[b]].tobytes(), blk))
+        assert (crc2.cpu().numpy().astype(np.uint32) == crc_h).all()
+        # host path: identical chunk stream + CRC chain of reference chunks.c:248-249, and back
+        stream, chain = ctx.encode_host(np.frombuffer(data, dtype=np.uint8))
+        exp_stream = bytearray()
+        exp_chain = 0
+        for b in range(nblk):
+            c = int.from_bytes(hdr_h[b, 264:268].tobytes(), "little")
+            exp_stream += hdr_h[b, :3].tobytes() + hdr_h[b, 4:].tobytes() + pay_h[b, :c].tobytes()
+            exp_chain = oracle.crc32c(hdr_h[b].tobytes(), exp_chain)
+            exp_chain = oracle.crc32c(data[b * block:(b + 1) * block], exp_chain)
+        assert stream.tobytes() == bytes(exp_stream), _first_diff(stream.tobytes(), bytes(exp_stream))
+        assert chain == exp_chain
+        plain, chain2 = ctx.decode_host(stream, n)
+        assert plain.tobytes() == data and chain2 == exp_chain
+        return ctx.stats()
+    finally:
+        ctx.close()
+
+
+def test_batched_small_blocks_vs_oracle(pkg, oracle, vocab):
+    rng = random.Random(8)
+    nrng = np.random.default_rng(8)
+    block = 16384
+    parts = [_text(pkg, vocab, 3 * block), nrng.integers(0, 256, 2 * block, dtype=np.uint8).tobytes(), _runs(rng, 2 * block),
+             b"0123456789abcdef" * (block // 16), bytes(block), (bytes(nrng.integers(0, 256, 251, dtype=np.uint8)) * 100)[:block],
+             _text(pkg, vocab, 777, seed=5)]
+    data = b"".join(parts)
+    _check_batch(pkg, oracle, data, block, max_batch=4)   # several internal batches + ragged last block
+    _check_batch(pkg, oracle, data, block, max_batch=64)  # one batch
+
+
+def test_batched_native_256k_blocks(pkg, oracle, vocab):
+    block = 256 * 1024  # the reference's BRA_MAX_CHUNK_SIZE
+    data = _text(pkg, vocab, 3 * block + 12345) + pkg.gen_random(block, 2).tobytes()
+    _check_batch(pkg, oracle, data, block, max_batch=8)
+
+
+def test_batched_1mib_text_and_random(pkg, oracle, vocab):
+    """BASELINE configs 2 and 3 at full block size: a few blocks compared bit for bit with the oracle,
+    all blocks round-tripped."""
+    block = 1 << 20
+    data = _text(pkg, vocab, 6 * block) + pkg.gen_random(2 * block, 2).tobytes()
+    st = _check_batch(pkg, oracle, data, block, max_batch=8, full_compare_blocks=[0, 5, 6])
+    assert st["bwt_rounds"] >= 1
+
+
+def test_batched_8mib_periodic(pkg, oracle):
+    """BASELINE config 4: exactly periodic (n/16-way rotation ties -> primary 0) and long-repeat blocks."""
+    import torch
+    block = 8 << 20
+    nrng = np.random.default_rng(4)
+    a = b"0123456789abcdef" * (block // 16)
+    pat = bytes(nrng.integers(0, 256, 251, dtype=np.uint8))
+    ctx = pkg.Context(0, block, 2)
+    try:
+        for data, primary in ((a, 0), ((pat * (block // 251 + 1))[:block], None)):
+            d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+            hdr, pay, crc = ctx.encode_device(d_in, block)
+            h = hdr.cpu().numpy()
+            if primary is not None:
+                assert int.from_bytes(h[:4].tobytes(), "little") == primary
+            # the oracle's linear-time decode chain must reproduce the input from the GPU-encoded block
+            c = int.from_bytes(h[264:268].tobytes(), "little")
+            plain = oracle.decode_block(h.tobytes(), pay[:c].cpu().numpy().tobytes(), block)
+            assert plain == data, _first_diff(plain, data)
+            assert int(crc.cpu().numpy().astype(np.uint32)[0]) == oracle.crc32c(data)
+            out, out_len, crc2, status = ctx.decode_device(hdr, pay, 1)
+            assert int(status[0]) == 0 and int(out_len[0]) == block
+            assert out.cpu().numpy().tobytes() == data
+    finally:
+        ctx.close()
+
+
+def test_decode_rejects_corrupt_blocks(pkg, oracle, vocab):
+    import torch
+    block = 16384
+    data = _text(pkg, vocab, 4 * block)
+    ctx = pkg.Context(0, block, 8)
+    try:
+        d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        hdr, pay, crc = ctx.encode_device(d_in, len(data))
+        hdr = hdr.clone()
+        h = hdr.view(4, 268)
+        h[1, 0:4] = torch.tensor([0xFF, 0xFF, 0xFF, 0x00], dtype=torch.uint8)   # primary index out of range
+        h[2, 264:268] = torch.tensor([1, 0, 0, 0], dtype=torch.uint8)           # payload far too short
+        out, out_len, crc2, status = ctx.decode_device(hdr, pay, 4)
+        s = status.cpu().numpy()
+        assert s[0] == 0 and s[3] == 0 and s[1] != 0 and s[2] != 0
+        assert out.cpu().numpy()[:block].tobytes() == data[:block]
+    finally:
+        ctx.close()

@@ -1,0 +1,109 @@
+"""CPU: the scalar logic the kernels share with the host (br-archive_b200/csrc/bra_hd.h, built as
+libbra_hostlogic.so) against the oracle: Huffman tree replay, canonical codes, decode tables,
+GF(2) CRC folding. This is the exact code one GPU thread per block executes."""
+import ctypes as C
+import random
+
+import numpy as np
+import pytest
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+
+
+@pytest.fixture(scope="module")
+def hl(pkg):
+    import os
+    if not os.path.exists(pkg.HOSTLOGIC_PATH):
+        pkg.build()
+    L = C.CDLL(pkg.HOSTLOGIC_PATH)
+    L.hl_gf_mul.restype = C.c_uint32
+    L.hl_gf_mul.argtypes = [C.c_uint32, C.c_uint32]
+    L.hl_crc_combine.restype = C.c_uint32
+    L.hl_crc_combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64]
+    L.hl_huf_lengths.restype = C.c_uint32
+    L.hl_huf_lengths.argtypes = [u32p, u8p]
+    L.hl_huf_canonical.argtypes = [u8p, u32p]
+    L.hl_huf_decode.restype = C.c_int
+    L.hl_huf_decode.argtypes = [u8p, u8p, C.c_uint32, C.c_uint32, u8p]
+    return L
+
+
+def _lengths(hl, freq):
+    f = np.ascontiguousarray(freq, dtype=np.uint32)
+    out = np.zeros(256, dtype=np.uint8)
+    k = hl.hl_huf_lengths(f.ctypes.data_as(u32p), out.ctypes.data_as(u8p))
+    return k, out
+
+
+def test_huffman_lengths_replay(hl, oracle):
+    rng = random.Random(5)
+    for it in range(1500):
+        k = rng.choice([1, 2, 3, 5, 17, 100, 256])
+        freq = np.zeros(256, dtype=np.uint32)
+        for s in rng.sample(range(256), k):
+            freq[s] = [rng.randrange(1, 4), rng.randrange(1, 1000), 1 << rng.randrange(20), rng.randrange(1, 1 << 24)][it % 4]
+        n, got = _lengths(hl, freq)
+        assert n == k
+        assert bytes(got) == bytes(oracle.huffman_lengths(freq)), (it, freq[freq > 0])
+    assert _lengths(hl, np.zeros(256, dtype=np.uint32))[0] == 0
+
+
+def test_huffman_lengths_fibonacci_depth(hl, oracle):
+    fib = [1, 1]
+    while len(fib) < 33:
+        fib.append(fib[-1] + fib[-2])
+    freq = np.zeros(256, dtype=np.uint32)
+    freq[10:10 + len(fib)] = fib
+    _, got = _lengths(hl, freq)
+    assert bytes(got) == bytes(oracle.huffman_lengths(freq))
+    assert got.max() == 32
+
+
+def test_canonical_codes(hl, oracle):
+    rng = random.Random(9)
+    for _ in range(300):
+        lengths = np.zeros(256, dtype=np.uint8)
+        for s in rng.sample(range(256), rng.choice([1, 2, 40, 256])):
+            lengths[s] = rng.randrange(1, 40)
+        got = np.zeros(256, dtype=np.uint32)
+        hl.hl_huf_canonical(lengths.ctypes.data_as(u8p), got.ctypes.data_as(u32p))
+        assert (got == oracle.huffman_canonical(lengths)).all()
+
+
+def test_decode_tables_roundtrip(hl, oracle):
+    rng = np.random.default_rng(3)
+    for it in range(60):
+        n = int(rng.integers(1, 5000))
+        k = int(rng.choice([1, 2, 3, 16, 256]))
+        p = rng.dirichlet(np.ones(k) * (0.05 if it % 2 else 1.0))
+        data = rng.choice(k, size=n, p=p).astype(np.uint8)
+        lengths, payload = oracle.huffman_encode(data.tobytes())
+        l = np.frombuffer(lengths, dtype=np.uint8).copy()
+        pay = np.frombuffer(payload, dtype=np.uint8).copy()
+        out = np.zeros(n, dtype=np.uint8)
+        rc = hl.hl_huf_decode(l.ctypes.data_as(u8p), pay.ctypes.data_as(u8p), len(pay), n, out.ctypes.data_as(u8p))
+        assert rc == 0 and out.tobytes() == data.tobytes()
+
+
+def test_decode_tables_reject_oversubscribed(hl):
+    l = np.zeros(256, dtype=np.uint8)
+    l[0:3] = 1  # three 1-bit codes cannot exist
+    out = np.zeros(4, dtype=np.uint8)
+    pay = np.zeros(4, dtype=np.uint8)
+    assert hl.hl_huf_decode(l.ctypes.data_as(u8p), pay.ctypes.data_as(u8p), 4, 4, out.ctypes.data_as(u8p)) == -1
+    l[:] = 0
+    l[7] = 33  # longer than the decoder supports
+    assert hl.hl_huf_decode(l.ctypes.data_as(u8p), pay.ctypes.data_as(u8p), 4, 1, out.ctypes.data_as(u8p)) == -1
+
+
+def test_crc_fold(hl, oracle):
+    rng = random.Random(1)
+    for _ in range(300):
+        d = bytes(rng.randrange(256) for _ in range(rng.randrange(1, 400)))
+        k = rng.randrange(len(d) + 1)
+        a, b = oracle.crc32c(d[:k]), oracle.crc32c(d[k:])
+        assert hl.hl_crc_combine(a, b, len(d) - k) == oracle.crc32c(d) == oracle.crc32c_combine(a, b, len(d) - k)
+    # long zero runs: combine with huge lengths must agree with the oracle's square-and-multiply
+    for ln in (1 << 20, (1 << 32) - 1, 123456789):
+        assert hl.hl_crc_combine(0x12345678, 0x9ABCDEF0, ln) == oracle.crc32c_combine(0x12345678, 0x9ABCDEF0, ln)
