@@ -60,7 +60,11 @@ __global__ void __launch_bounds__(256) bwt_period_kernel(const uint8_t* __restri
             if (j >= n) j -= n;
             ne = T[l] != T[j];
         }
-        if (__any_sync(BRA_FULL, ne)) continue;  // same outcome in every warp of the CTA
+        if (__any_sync(BRA_FULL, ne))  // same outcome in every warp of the CTA: d is not a period
+        {
+            if (threadIdx.x == 0) bad[(uint64_t) b * bad_stride + di] = 1;
+            continue;
+        }
         bool mism = false;
         for (uint32_t i = tile0 + threadIdx.x; i < tend; i += 256)
         {
