@@ -163,7 +163,8 @@ struct HufDecArgs
     uint64_t        out_stride;  // must hold orig_size bytes per block
     bra_huf_dec_t*  d_tabs;
     uint32_t*       d_err;  // per block, zeroed by the caller
-    uint8_t *       d_sub_start, *d_sub_count;           // nblk*seqs*256
+    uint8_t*        d_sub_start;   // nblk*seqs*256
+    uint16_t*       d_sub_count;   // nblk*seqs*256
     uint32_t *      d_seq_entry, *d_seq_exit, *d_seq_count;  // nblk*seqs
     uint32_t *      d_end_bit, *d_changed;
     uint32_t*       h_sweeps;

@@ -475,34 +475,50 @@ __global__ void __launch_bounds__(IB_THREADS)
     } while (idx != pi && (idx % R) != 0);
     const uint32_t succ = (idx == pi) ? K : idx / R;
     walk[(uint64_t) b * kmax + w] = make_uint2(steps, succ);
-    woff[(uint64_t) b * kmax + w] = IB_INVALID;
 }
 
 // Stitch: order the walks from the primary row. If the chain closes before n bytes are covered the
 // text is a repetition of that orbit (periodic input): orbit[b] < n and every walk is replicated.
-__global__ void ibwt_stitch_kernel(const uint32_t* __restrict__ len, uint32_t R, uint32_t kmax, const uint2* __restrict__ walk,
-                                   uint32_t* __restrict__ woff, uint32_t* __restrict__ orbit, uint32_t nblk)
+// One CTA per block: the walk table (at most 8193 entries) is staged in shared memory so that the
+// dependent chain runs at shared-memory latency instead of one global round trip per walk.
+#define IB_STITCH_THREADS 256
+__global__ void __launch_bounds__(IB_STITCH_THREADS)
+    ibwt_stitch_kernel(const uint32_t* __restrict__ len, uint32_t R, uint32_t kmax, const uint2* __restrict__ walk, uint32_t* __restrict__ woff,
+                       uint32_t* __restrict__ orbit)
 {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= nblk) return;
+    extern __shared__ uint32_t s_dyn[];  // [0,kmax): walk length; [kmax,2kmax): successor; [2kmax,3kmax): offset
+    const uint32_t b = blockIdx.x;
     const uint32_t n = len[b];
     if (n == 0)
     {
-        orbit[b] = 0;
+        if (threadIdx.x == 0) orbit[b] = 0;
         return;
     }
-    const uint32_t K   = ib_rows(n, R);
-    const uint2*   wk  = walk + (uint64_t) b * kmax;
-    uint32_t*      off = woff + (uint64_t) b * kmax;
-    uint32_t w = K, o = 0;
-    while (o < n && off[w] == IB_INVALID)
+    const uint32_t K    = ib_rows(n, R);
+    uint32_t*      slen = s_dyn;
+    uint32_t*      ssuc = s_dyn + kmax;
+    uint32_t*      soff = s_dyn + 2 * kmax;
+    for (uint32_t w = threadIdx.x; w <= K; w += IB_STITCH_THREADS)
     {
-        const uint2 e = wk[w];
-        off[w]        = o;
-        o += e.x;
-        w = e.y;
+        const uint2 e = walk[(uint64_t) b * kmax + w];
+        slen[w]       = e.x;
+        ssuc[w]       = e.y;
+        soff[w]       = IB_INVALID;
     }
-    orbit[b] = o;  // == n unless the chain closed early
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        uint32_t w = K, o = 0;
+        while (o < n && soff[w] == IB_INVALID)
+        {
+            soff[w] = o;
+            o += slen[w];
+            w = ssuc[w];
+        }
+        orbit[b] = o;  // == n unless the chain closed early
+    }
+    __syncthreads();
+    for (uint32_t w = threadIdx.x; w <= K; w += IB_STITCH_THREADS) woff[(uint64_t) b * kmax + w] = soff[w];
 }
 
 // Walk 2: emit F[idx] = W[idx] & 0xFF at the stitched offsets (replicated every `orbit` bytes).
@@ -559,7 +575,14 @@ bool bwt_inverse_batch(const BwtInvArgs& a, cudaStream_t st)
     if (!radix_pass_u8_index_packed(a.d_in, a.d_W, a.stride, a.d_len, a.max_n, a.nblk, a.d_hist, st)) return false;
     const dim3 grid(bra_div_up(kmax, IB_THREADS), a.nblk);
     BRA_LAUNCH(P_IBWT_WALK_LEN, st, ibwt_walk_len_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff));
-    BRA_LAUNCH(P_IBWT_STITCH, st, ibwt_stitch_kernel<<<bra_div_up(a.nblk, 32), 32, 0, st>>>(a.d_len, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.nblk));
+    const size_t stitch_smem = (size_t) kmax * 3 * sizeof(uint32_t);
+    static bool stitch_attr_set = false;
+    if (!stitch_attr_set)
+    {
+        BRA_CUDA_TRY(cudaFuncSetAttribute(ibwt_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8200 * 4));
+        stitch_attr_set = true;
+    }
+    BRA_LAUNCH(P_IBWT_STITCH, st, ibwt_stitch_kernel<<<a.nblk, IB_STITCH_THREADS, stitch_smem, st>>>(a.d_len, R, kmax, a.d_walk, a.d_woff, a.d_orbit));
     BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_walk_emit_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_out));
     BRA_CUDA_TRY(cudaGetLastError());
     return true;

@@ -246,11 +246,13 @@ bool huf_encode_batch(const HufEncArgs& a, cudaStream_t st)
 // ================================================================================================
 // DECODE
 // ================================================================================================
-#define HD_SUB_BITS 128u
+#define HD_SUB_BITS 1024u
 #define HD_THREADS 256
-#define HD_SEQ_BITS (HD_SUB_BITS * HD_THREADS)  // 32768 bits = 4 KiB of payload per CTA
+#define HD_SEQ_BITS (HD_SUB_BITS * HD_THREADS)  // 262144 bits = 32 KiB of payload per CTA
 #define HD_SEQ_BYTES (HD_SEQ_BITS / 8)
-#define HD_SMEM_WORDS (HD_SEQ_BYTES / 4 + 4)    // + look-ahead for codes crossing the sequence end
+#define HD_ROW_WORDS (HD_SUB_BITS / 32)         // 32 words per subsequence
+#define HD_SMEM_WORDS (HD_SEQ_BYTES / 4 + HD_ROW_WORDS)  // + one row of look-ahead for codes crossing the sequence end
+#define HD_LUT_BITS 11
 
 // per-block decode tables, built once per block by one thread
 __global__ void __launch_bounds__(32) huf_dec_tables_kernel(const uint8_t* __restrict__ hdr, bra_huf_dec_t* __restrict__ tabs, uint32_t* __restrict__ err)
@@ -265,22 +267,18 @@ __global__ void __launch_bounds__(32) huf_dec_tables_kernel(const uint8_t* __res
     }
 }
 
-// big-endian 32-bit window starting at bit `pos` of the CTA's staged payload words
-__device__ __forceinline__ uint32_t hd_peek(const uint32_t* sw, uint32_t pos)
-{
-    const uint32_t w = pos >> 5, o = pos & 31u;
-    const uint32_t a = sw[w], b2 = sw[w + 1];
-    return o ? (a << o) | (b2 >> (32u - o)) : a;
-}
-
 struct HdShared
 {
-    uint32_t      words[HD_SMEM_WORDS];
+    uint32_t      words[HD_SMEM_WORDS];   // payload slice, big-endian words, swizzled (see hd_word)
     bra_huf_dec_t tab;
+    uint16_t      lut[1 << HD_LUT_BITS];  // (sym << 8) | len for codes of at most HD_LUT_BITS bits, 0 = longer / invalid
     uint32_t      start[HD_THREADS + 1];  // bit offset (relative to the sequence start) of the first codeword of each subsequence
     uint32_t      red[34];
-    int           changed;
 };
+
+// Thread k streams through words 32k..32k+31: unswizzled, all 256 threads would sit on one bank.
+// Word i lives at (i & ~31) | ((i ^ (i >> 5)) & 31), so that threads at the same column hit 32 banks.
+__device__ __forceinline__ uint32_t hd_word(const HdShared& S, uint32_t i) { return S.words[(i & ~31u) | ((i ^ (i >> 5)) & 31u)]; }
 
 __device__ __forceinline__ void hd_stage(HdShared& S, const uint8_t* __restrict__ pay, uint32_t seq, uint32_t cbytes)
 {
@@ -296,8 +294,56 @@ __device__ __forceinline__ void hd_stage(HdShared& S, const uint8_t* __restrict_
             v = __byte_perm(pw[i], 0, 0x0123);
             if (bo + 4 > cbytes) v &= 0xFFFFFFFFu << ((bo + 4 - cbytes) * 8);
         }
-        S.words[i] = v;
+        S.words[(i & ~31u) | ((i ^ (i >> 5)) & 31u)] = v;
     }
+}
+
+// first-level table: one lookup resolves every code of at most HD_LUT_BITS bits
+__device__ __forceinline__ void hd_build_lut(HdShared& S)
+{
+    for (uint32_t i = threadIdx.x; i < (1u << HD_LUT_BITS); i += HD_THREADS)
+    {
+        uint8_t        sym = 0;
+        const uint32_t l   = bra_huf_decode_one(&S.tab, i << (32 - HD_LUT_BITS), &sym);
+        S.lut[i]           = (l && l <= HD_LUT_BITS) ? (uint16_t) ((sym << 8) | l) : (uint16_t) 0;
+    }
+}
+
+// bit reader over the staged words: 64-bit left-aligned buffer, refilled a word at a time
+struct HdReader
+{
+    uint64_t buf;
+    uint32_t avail, next_word;
+};
+__device__ __forceinline__ void hd_open(const HdShared& S, HdReader& R, uint32_t pos)
+{
+    const uint32_t w = pos >> 5, o = pos & 31u;
+    R.buf       = (((uint64_t) hd_word(S, w) << 32) | hd_word(S, w + 1)) << o;
+    R.avail     = 64u - o;
+    R.next_word = w + 2;
+}
+__device__ __forceinline__ void hd_skip(const HdShared& S, HdReader& R, uint32_t l)
+{
+    R.buf <<= l;
+    R.avail -= l;
+    if (R.avail <= 32u)
+    {
+        const uint32_t nw = R.next_word < HD_SMEM_WORDS ? hd_word(S, R.next_word) : 0u;
+        R.buf |= (uint64_t) nw << (32u - R.avail);
+        R.avail += 32u;
+        ++R.next_word;
+    }
+}
+__device__ __forceinline__ uint32_t hd_decode(const HdShared& S, const HdReader& R, uint8_t* sym)
+{
+    const uint32_t w = (uint32_t) (R.buf >> 32);
+    const uint32_t e = S.lut[w >> (32 - HD_LUT_BITS)];
+    if (e)
+    {
+        *sym = (uint8_t) (e >> 8);
+        return e & 0xFFu;
+    }
+    return bra_huf_decode_one(&S.tab, w, sym);
 }
 
 // Decode subsequence k from relative bit `pos` until crossing its end (or the end of the payload).
@@ -307,18 +353,24 @@ __device__ __forceinline__ uint32_t hd_walk(const HdShared& S, uint32_t pos, uin
 {
     uint32_t c = 0;
     *dead      = false;
-    while (pos < sub_end && pos < data_end)
+    if (pos < sub_end && pos < data_end)
     {
-        uint8_t        sym;
-        const uint32_t l = bra_huf_decode_one(&S.tab, hd_peek(S.words, pos), &sym);
-        if (l == 0)
+        HdReader R;
+        hd_open(S, R, pos);
+        while (pos < sub_end && pos < data_end)
         {
-            *dead = true;
-            break;
+            uint8_t        sym;
+            const uint32_t l = hd_decode(S, R, &sym);
+            if (l == 0)
+            {
+                *dead = true;
+                break;
+            }
+            if (pos + l > data_end) break;  // incomplete trailing code: padding
+            hd_skip(S, R, l);
+            pos += l;
+            ++c;
         }
-        if (pos + l > data_end) break;  // incomplete trailing code: padding
-        pos += l;
-        ++c;
     }
     *count = c;
     return pos;
@@ -329,7 +381,7 @@ __device__ __forceinline__ uint32_t hd_walk(const HdShared& S, uint32_t pos, uin
 //   seq_exit[b][seq]  : where its last subsequence crossed into the next CTA's sequence (relative to that sequence)
 __global__ void __launch_bounds__(HD_THREADS)
     huf_dec_sync_kernel(const uint8_t* __restrict__ pay, uint64_t pay_stride, const uint32_t* __restrict__ clen, const bra_huf_dec_t* __restrict__ tabs,
-                        const uint32_t* __restrict__ err, uint32_t seqs, uint8_t* __restrict__ sub_start, uint8_t* __restrict__ sub_count,
+                        const uint32_t* __restrict__ err, uint32_t seqs, uint8_t* __restrict__ sub_start, uint16_t* __restrict__ sub_count,
                         uint32_t* __restrict__ seq_entry, uint32_t* __restrict__ seq_exit, uint32_t* __restrict__ seq_count,
                         uint32_t* __restrict__ changed_flag)
 {
@@ -365,6 +417,8 @@ __global__ void __launch_bounds__(HD_THREADS)
         S.start[HD_THREADS] = first_run ? HD_SEQ_BITS : HD_SEQ_BITS + seq_exit[sidx];
     }
     __syncthreads();
+    hd_build_lut(S);
+    __syncthreads();
 
     uint32_t used  = 0xFFFFFFFFu;  // start value my current (exit, count) were computed from
     uint32_t myexit = 0, mycount = 0;
@@ -397,7 +451,7 @@ __global__ void __launch_bounds__(HD_THREADS)
         if (!__syncthreads_or(ch)) break;
     }
     sub_start[sub_idx] = (uint8_t) (S.start[k] - k * HD_SUB_BITS);
-    sub_count[sub_idx] = (uint8_t) mycount;
+    sub_count[sub_idx] = (uint16_t) mycount;
     uint32_t total;
     block_excl_add(mycount, S.red, &total);
     if (k == 0)
@@ -448,7 +502,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(HD_THREADS)
     huf_dec_write_kernel(const uint8_t* __restrict__ pay, uint64_t pay_stride, const uint32_t* __restrict__ clen, const uint8_t* __restrict__ hdr,
                          const bra_huf_dec_t* __restrict__ tabs, uint32_t seqs, const uint8_t* __restrict__ sub_start,
-                         const uint8_t* __restrict__ sub_count, const uint32_t* __restrict__ seq_off, uint8_t* __restrict__ out,
+                         const uint16_t* __restrict__ sub_count, const uint32_t* __restrict__ seq_off, uint8_t* __restrict__ out,
                          uint64_t out_stride, uint32_t* __restrict__ end_bit, uint32_t* __restrict__ err)
 {
     __shared__ HdShared S;
@@ -463,20 +517,25 @@ __global__ void __launch_bounds__(HD_THREADS)
     for (uint32_t i = threadIdx.x; i < sizeof(bra_huf_dec_t) / 4; i += HD_THREADS)
         reinterpret_cast<uint32_t*>(&S.tab)[i] = reinterpret_cast<const uint32_t*>(&tabs[b])[i];
     hd_stage(S, pay + (uint64_t) b * pay_stride, seq, c);
+    __syncthreads();
+    hd_build_lut(S);
     const uint32_t k       = threadIdx.x;
     const uint64_t sub_idx = sidx * HD_THREADS + k;
     const uint32_t cnt     = sub_count[sub_idx];
     uint32_t       dummy;
-    uint32_t       o   = o0 + block_excl_add(cnt, S.red, &dummy);  // also orders the staging writes
+    uint32_t       o   = o0 + block_excl_add(cnt, S.red, &dummy);  // also orders the staging / table writes
     uint32_t       pos = k * HD_SUB_BITS + sub_start[sub_idx];
     uint8_t*       ob  = out + (uint64_t) b * out_stride;
     const uint32_t sub_end  = (k + 1) * HD_SUB_BITS;
     const uint32_t data_end = min((uint32_t) HD_SEQ_BITS + 64u, (c - seq * HD_SEQ_BYTES) * 8u);
+    if (!(pos < sub_end && pos < data_end && o < orig)) return;
+    HdReader R;
+    hd_open(S, R, pos);
     // same walk as hd_walk (so the counts agree), now storing the symbols
     while (pos < sub_end && pos < data_end && o < orig)
     {
         uint8_t        sym = 0;
-        const uint32_t l   = bra_huf_decode_one(&S.tab, hd_peek(S.words, pos), &sym);
+        const uint32_t l   = hd_decode(S, R, &sym);
         if (l == 0)
         {
             err[b] = 1;  // no codeword matches before orig_size symbols: "invalid code sequence" (bra_huffman.c:466-470)
@@ -484,6 +543,7 @@ __global__ void __launch_bounds__(HD_THREADS)
         }
         if (pos + l > data_end) break;
         ob[o++] = sym;
+        hd_skip(S, R, l);
         pos += l;
         if (o == orig) end_bit[b] = seq * HD_SEQ_BITS + pos;
     }

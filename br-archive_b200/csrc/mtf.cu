@@ -20,38 +20,65 @@ namespace bra {
 #define MTF_SEG 4096
 #define MTF_WARPS 4  // warps (= segments) per CTA
 
-// ---- warp-resident list: lane l holds entries 8l..8l+7, entry 8l in the low byte of `lo` --------
+// ---- warp-resident list ---------------------------------------------------------------------------
+// Entries 0..7 (where almost every hit lands on BWT output) are replicated in every lane as the
+// uniform pair (f0, f1): hits there cost no cross-lane traffic. Entries 8..255 are distributed,
+// lane l (1..31) holding entries 8l..8l+7 in (lo, hi), entry 8l in the low byte of lo. Lane 0's
+// (lo, hi) are unused.
 struct WarpList
 {
-    uint32_t lo, hi;
+    uint32_t f0, f1;  // uniform: entries 0-3, 4-7
+    uint32_t lo, hi;  // per lane: entries 8l..8l+3, 8l+4..8l+7
 };
 
+__device__ __forceinline__ WarpList wl_from_lane_words(uint32_t lo, uint32_t hi)
+{
+    WarpList r;
+    r.lo = lo;
+    r.hi = hi;
+    r.f0 = __shfl_sync(BRA_FULL, lo, 0);
+    r.f1 = __shfl_sync(BRA_FULL, hi, 0);
+    return r;
+}
 __device__ __forceinline__ WarpList wl_identity()
 {
     const uint32_t b = lane_id() * 8;
-    WarpList       r;
-    r.lo = (b) | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24);
-    r.hi = (b + 4) | ((b + 5) << 8) | ((b + 6) << 16) | ((b + 7) << 24);
-    return r;
+    return wl_from_lane_words((b) | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24), (b + 4) | ((b + 5) << 8) | ((b + 6) << 16) | ((b + 7) << 24));
 }
 __device__ __forceinline__ WarpList wl_load(const uint8_t* p)  // 256 bytes, 8-byte aligned
 {
     const uint2 v = reinterpret_cast<const uint2*>(p)[lane_id()];
-    WarpList    r;
-    r.lo = v.x;
-    r.hi = v.y;
-    return r;
+    return wl_from_lane_words(v.x, v.y);
 }
-__device__ __forceinline__ void wl_store(uint8_t* p, WarpList l) { reinterpret_cast<uint2*>(p)[lane_id()] = make_uint2(l.lo, l.hi); }
+__device__ __forceinline__ void wl_store(uint8_t* p, const WarpList& l)
+{
+    reinterpret_cast<uint2*>(p)[lane_id()] = lane_id() == 0 ? make_uint2(l.f0, l.f1) : make_uint2(l.lo, l.hi);
+}
 
-// Move the entry at list position `pos` (warp-uniform) to the front; `sym` is its value.
-__device__ __forceinline__ void wl_move_to_front(WarpList& L, uint32_t pos, uint32_t sym)
+// 0x80 in the lowest byte of `w` equal to the replicated byte s4 (higher marks may be spurious: use the lowest)
+__device__ __forceinline__ uint32_t byte_match(uint32_t w, uint32_t s4)
+{
+    const uint32_t t = w ^ s4;
+    return (t - 0x01010101u) & ~t & 0x80808080u;
+}
+
+// front part: move entry p (1..7, uniform) to position 0; x is its value
+__device__ __forceinline__ void wl_rotate_front(WarpList& L, uint32_t p, uint32_t x)
+{
+    const uint64_t v    = ((uint64_t) L.f1 << 32) | L.f0;
+    const uint64_t low  = (p == 7) ? ~0ull : ((1ull << ((p + 1) * 8)) - 1ull);
+    const uint64_t nv   = (v & ~low) | (((v << 8) | x) & low);
+    L.f0 = (uint32_t) nv;
+    L.f1 = (uint32_t) (nv >> 32);
+}
+
+// distributed part: entry at position pos >= 8 (uniform) moves to the front; x is its value
+__device__ __forceinline__ void wl_move_far(WarpList& L, uint32_t pos, uint32_t x)
 {
     const uint32_t lane = lane_id();
     const uint32_t hl = pos >> 3, hb = pos & 7u;
-    // byte that enters this lane from the left neighbour (lane 0 receives the symbol itself)
-    uint32_t incoming = __shfl_up_sync(BRA_FULL, L.hi >> 24, 1);
-    if (lane == 0) incoming = sym;
+    // byte entering each lane from its left neighbour; lane 1 receives entry 7 of the front part
+    uint32_t incoming = __shfl_up_sync(BRA_FULL, (lane == 0 ? L.f1 : L.hi) >> 24, 1);
     const uint64_t v       = ((uint64_t) L.hi << 32) | L.lo;
     const uint64_t shifted = (v << 8) | incoming;
     uint64_t       nv      = v;
@@ -64,27 +91,56 @@ __device__ __forceinline__ void wl_move_to_front(WarpList& L, uint32_t pos, uint
     }
     L.lo = (uint32_t) nv;
     L.hi = (uint32_t) (nv >> 32);
+    L.f1 = (L.f1 << 8) | (L.f0 >> 24);
+    L.f0 = (L.f0 << 8) | x;
 }
 
-// position of `sym` (warp-uniform) in the list
-__device__ __forceinline__ uint32_t wl_find(const WarpList& L, uint32_t sym)
+// encode one symbol (uniform): returns its rank and updates the list
+__device__ __forceinline__ uint32_t wl_encode(WarpList& L, uint32_t x)
 {
-    const uint32_t s4 = sym * 0x01010101u;
-    const uint32_t m0 = __vcmpeq4(L.lo, s4), m1 = __vcmpeq4(L.hi, s4);
-    const uint32_t ball = __ballot_sync(BRA_FULL, (m0 | m1) != 0u);
+    const uint32_t s4 = x * 0x01010101u;
+    const uint32_t z0 = byte_match(L.f0, s4);
+    if (z0)
+    {
+        const uint32_t p = (__ffs(z0) - 1) >> 3;
+        if (p) wl_rotate_front(L, p, x);
+        return p;
+    }
+    const uint32_t z1 = byte_match(L.f1, s4);
+    if (z1)
+    {
+        const uint32_t p = 4 + ((__ffs(z1) - 1) >> 3);
+        wl_rotate_front(L, p, x);
+        return p;
+    }
+    const uint32_t m0 = byte_match(L.lo, s4), m1 = byte_match(L.hi, s4);
+    const uint32_t ball = __ballot_sync(BRA_FULL, lane_id() != 0 && (m0 | m1) != 0u);
     const uint32_t hl   = __ffs(ball) - 1;
     const uint32_t in_lane = m0 ? ((__ffs(m0) - 1) >> 3) : (4 + ((__ffs(m1) - 1) >> 3));
-    return hl * 8 + __shfl_sync(BRA_FULL, in_lane, hl);
+    const uint32_t pos = hl * 8 + __shfl_sync(BRA_FULL, in_lane, hl);
+    wl_move_far(L, pos, x);
+    return pos;
 }
-// value at list position `pos` (warp-uniform)
-__device__ __forceinline__ uint32_t wl_get(const WarpList& L, uint32_t pos)
+
+// decode one rank (uniform): returns the symbol and updates the list
+__device__ __forceinline__ uint32_t wl_decode(WarpList& L, uint32_t r)
 {
-    const uint32_t w = (pos & 4u) ? L.hi : L.lo;
-    return __shfl_sync(BRA_FULL, (w >> ((pos & 3u) * 8)) & 0xFFu, pos >> 3);
+    if (r < 8)
+    {
+        const uint32_t x = ((r & 4u ? L.f1 : L.f0) >> ((r & 3u) * 8)) & 0xFFu;
+        if (r) wl_rotate_front(L, r, x);
+        return x;
+    }
+    const uint32_t w = (r & 4u) ? L.hi : L.lo;
+    const uint32_t x = __shfl_sync(BRA_FULL, (w >> ((r & 3u) * 8)) & 0xFFu, r >> 3);
+    wl_move_far(L, r, x);
+    return x;
 }
 
 // ---- segment replay (shared by summary/apply) ---------------------------------------------------
 // ENCODE: in = symbols, out = ranks. DECODE: in = ranks, out = symbols. out may be null (summary).
+// Four symbols travel per shuffle; a word that repeats the front symbol (encode) or is all-zero
+// ranks (decode) -- the common case on BWT output -- is retired without touching the list.
 template <bool ENCODE, bool WRITE>
 __device__ __forceinline__ void mtf_replay(WarpList& L, const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint32_t m)
 {
@@ -98,30 +154,35 @@ __device__ __forceinline__ void mtf_replay(WarpList& L, const uint8_t* __restric
         else
             for (uint32_t k = 0; k < 4; ++k)
                 if (base + lane * 4 + k < m) wrd |= (uint32_t) in[base + lane * 4 + k] << (8 * k);
-        uint32_t ow = 0;
-        for (uint32_t i = 0; i < cnt; ++i)
+        uint32_t       myow   = 0;
+        const uint32_t nwords = (cnt + 3) >> 2;
+        for (uint32_t wi = 0; wi < nwords; ++wi)
         {
-            const uint32_t x = (__shfl_sync(BRA_FULL, wrd, i >> 2) >> ((i & 3u) * 8)) & 0xFFu;
-            uint32_t       res;
-            if (ENCODE)
-            {
-                res = wl_find(L, x);
-                wl_move_to_front(L, res, x);
-            }
+            const uint32_t w    = __shfl_sync(BRA_FULL, wrd, wi);
+            const uint32_t nsym = min(4u, cnt - wi * 4);
+            const uint32_t fr   = L.f0 & 0xFFu;
+            uint32_t       ow;
+            if (nsym == 4 && (ENCODE ? (w == fr * 0x01010101u) : (w == 0u)))
+                ow = ENCODE ? 0u : fr * 0x01010101u;
             else
             {
-                res = wl_get(L, x);
-                wl_move_to_front(L, x, res);
+                ow = 0;
+                for (uint32_t k = 0; k < nsym; ++k)
+                {
+                    const uint32_t x   = (w >> (k * 8)) & 0xFFu;
+                    const uint32_t res = ENCODE ? wl_encode(L, x) : wl_decode(L, x);
+                    ow |= res << (k * 8);
+                }
             }
-            if (WRITE && lane == (i >> 2)) ow |= res << ((i & 3u) * 8);
+            if (WRITE && lane == wi) myow = ow;
         }
         if (WRITE)
         {
             if (base + lane * 4 + 4 <= m)
-                *reinterpret_cast<uint32_t*>(out + base + lane * 4) = ow;
+                *reinterpret_cast<uint32_t*>(out + base + lane * 4) = myow;
             else
                 for (uint32_t k = 0; k < 4; ++k)
-                    if (base + lane * 4 + k < m) out[base + lane * 4 + k] = (ow >> (8 * k)) & 0xFFu;
+                    if (base + lane * 4 + k < m) out[base + lane * 4 + k] = (myow >> (8 * k)) & 0xFFu;
         }
     }
 }

@@ -68,7 +68,8 @@ struct EncWs
 };
 struct DecWs
 {
-    uint8_t * R, *M, *L, *summ, *state, *sub_start, *sub_count, *t_exit, *t_entry;
+    uint8_t * R, *M, *L, *summ, *state, *sub_start, *t_exit, *t_entry;
+    uint16_t* sub_count;
     uint32_t *W, *hist, *rlen, *clen, *nlen, *primary, *err, *seq_entry, *seq_exit, *seq_count, *end_bit, *changed, *t_tok, *t_ocnt, *woff,
         *orbit;
     uint2*         walk;
@@ -111,7 +112,7 @@ static void carve_dec(Arena& A, uint32_t S, uint32_t nb, DecWs& w)
     const uint64_t segs = mtf_segments(S);
     w.summ = A.take<uint8_t>(nb * segs * 256); w.state = A.take<uint8_t>(nb * segs * 256);
     const uint64_t seqs = huf_dec_seqs((uint32_t) PS);
-    w.sub_start = A.take<uint8_t>(nb * seqs * huf_dec_subs_per_seq()); w.sub_count = A.take<uint8_t>(nb * seqs * huf_dec_subs_per_seq());
+    w.sub_start = A.take<uint8_t>(nb * seqs * huf_dec_subs_per_seq()); w.sub_count = A.take<uint16_t>(nb * seqs * huf_dec_subs_per_seq());
     w.seq_entry = A.take<uint32_t>(nb * seqs); w.seq_exit = A.take<uint32_t>(nb * seqs); w.seq_count = A.take<uint32_t>(nb * seqs);
     const uint64_t rt = rle_dec_tiles((uint32_t) RS);
     w.t_exit = A.take<uint8_t>(nb * rt * rle_dec_entries()); w.t_entry = A.take<uint8_t>(nb * rt);

@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(1024) rs_scan_kernel(uint32_t* __restrict__ hi
 // OUT_MODE 0: write keys_out and vals_out; 1: write vals_out only;
 //          2: write packed (val << 8) | key8 into vals_out (inverse-BWT "next row | byte" word)
 template <typename KeyT, bool IMPLICIT_VALS, int OUT_MODE>
-__global__ void __launch_bounds__(RS_THREADS)
+__global__ void __launch_bounds__(RS_THREADS, 4)
     rs_scatter_kernel(const KeyT* __restrict__ keys, const uint32_t* __restrict__ vals, KeyT* __restrict__ keys_out,
                       uint32_t* __restrict__ vals_out, uint64_t stride, const uint32_t* __restrict__ len,
                       const uint8_t* __restrict__ skip, uint32_t shift, uint32_t tiles, const uint32_t* __restrict__ hist)
@@ -115,16 +115,13 @@ __global__ void __launch_bounds__(RS_THREADS)
     __syncthreads();
 
     // warp w owns elements [w*512, w*512+512) of the tile, visited in 16 rounds of 32 (memory order)
-    KeyT     k[RS_ITEMS];
-    uint32_t v[RS_ITEMS];
-    uint32_t rk[RS_ITEMS];  // rank among equal digits inside the warp
+    KeyT           k[RS_ITEMS];
+    unsigned short rk[RS_ITEMS];  // rank among equal digits inside the warp (< 512)
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r)
     {
         const uint32_t e = w * 512 + r * 32 + l;
-        const bool     ok = e < tn;
-        k[r] = ok ? keys[base + tile0 + e] : (KeyT) 0;
-        v[r] = IMPLICIT_VALS ? (tile0 + e) : (ok ? vals[base + tile0 + e] : 0u);
+        k[r]             = e < tn ? keys[base + tile0 + e] : (KeyT) 0;
     }
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r)
@@ -142,7 +139,7 @@ __global__ void __launch_bounds__(RS_THREADS)
             wcnt[w][d] = old + __popc(peers);
         }
         old   = __shfl_sync(BRA_FULL, old, leader);
-        rk[r] = old + before;
+        rk[r] = (unsigned short) (old + before);
         __syncwarp();
     }
     __syncthreads();
@@ -173,7 +170,7 @@ __global__ void __launch_bounds__(RS_THREADS)
             const uint32_t d   = rs_digit(k[r], shift);
             const uint32_t pos = dstart[d] + wcnt[w][d] + rk[r];
             skey[pos]          = k[r];
-            sval[pos]          = v[r];
+            sval[pos]          = IMPLICIT_VALS ? (tile0 + e) : vals[base + tile0 + e];  // values are only touched here (keeps registers low)
         }
     }
     __syncthreads();
