@@ -12,7 +12,7 @@ namespace bra {
 // ---- prof.cu: launch accounting (see include/bra_b200.h, bra_b200_prof_*) ------------------------
 enum ProfId
 {
-    P_CRC, P_RS_HIST, P_RS_SCAN, P_RS_SCATTER, P_BWT_PERIOD, P_BWT_KEYS, P_BWT_HEADS, P_BWT_RANKS, P_BWT_PREPARE, P_BWT_GATHER, P_BWT_MISC,
+    P_CRC, P_RS_HIST, P_RS_SCAN, P_RS_SCATTER, P_RS_SCATTER_U8, P_BWT_PERIOD, P_BWT_KEYS, P_BWT_HEADS, P_BWT_RANKS, P_BWT_PREPARE, P_BWT_GATHER, P_BWT_MISC,
     P_MTF_SUMMARY, P_MTF_SCAN, P_MTF_APPLY, P_RLE_ENC_HEADS, P_RLE_ENC_LIT, P_RLE_ENC_SIZE, P_RLE_ENC_EMIT, P_RLE_DEC_EXIT, P_RLE_DEC_CHAIN,
     P_RLE_DEC_MARK, P_RLE_DEC_EXPAND, P_HUF_HIST, P_HUF_BUILD, P_HUF_BITS, P_HUF_PACK, P_HUF_DEC_TABLES, P_HUF_DEC_SYNC, P_HUF_DEC_SCAN,
     P_HUF_DEC_WRITE, P_HUF_DEC_TRAILING, P_IBWT_WALK_LEN, P_IBWT_STITCH, P_IBWT_WALK_EMIT, P_GLUE, P_COUNT
@@ -39,7 +39,7 @@ bool crc_headers(const uint8_t* d_hdr, uint32_t item_bytes, uint32_t nitems, uin
 // ---- sort.cu ------------------------------------------------------------------------------
 size_t radix_hist_bytes(uint32_t max_len, uint32_t nblk);
 bool   radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t stride,
-                      const uint32_t* d_len, const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t* d_hist,
+                      const uint32_t* d_len, const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t bits, uint32_t* d_hist,
                       cudaStream_t st);
 bool   radix_pass_u8_index_packed(const uint8_t* keys, uint32_t* packed_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len,
                                   uint32_t nblk, uint32_t* d_hist, cudaStream_t st);

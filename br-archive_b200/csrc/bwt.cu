@@ -397,7 +397,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, kA, vA));
     for (uint32_t shift = 0; shift < 32; shift += 8)
     {
-        if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, shift, a.d_hist, st)) return false;
+        if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, shift, 8, a.d_hist, st)) return false;
         std::swap(kA, kB);
         std::swap(vA, vB);
     }
@@ -426,9 +426,11 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, h, a.stride, a.d_period, a.d_done, kB, vB));
         std::swap(kA, kB);
         std::swap(vA, vB);
-        for (uint32_t shift = 0; shift < key_bits; shift += 8)
+        // ranks below 2^20 sort in two 10-bit passes, smaller or larger blocks in 8-bit passes
+        const uint32_t digit = (key_bits > 16 && key_bits <= 20) ? 10u : 8u;
+        for (uint32_t shift = 0; shift < key_bits; shift += digit)
         {
-            if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, shift, a.d_hist, st)) return false;
+            if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, shift, digit, a.d_hist, st)) return false;
             std::swap(kA, kB);
             std::swap(vA, vB);
         }
@@ -576,12 +578,7 @@ bool bwt_inverse_batch(const BwtInvArgs& a, cudaStream_t st)
     const dim3 grid(bra_div_up(kmax, IB_THREADS), a.nblk);
     BRA_LAUNCH(P_IBWT_WALK_LEN, st, ibwt_walk_len_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff));
     const size_t stitch_smem = (size_t) kmax * 3 * sizeof(uint32_t);
-    static bool stitch_attr_set = false;
-    if (!stitch_attr_set)
-    {
-        BRA_CUDA_TRY(cudaFuncSetAttribute(ibwt_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8200 * 4));
-        stitch_attr_set = true;
-    }
+    BRA_CUDA_TRY(cudaFuncSetAttribute(ibwt_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8200 * 4));
     BRA_LAUNCH(P_IBWT_STITCH, st, ibwt_stitch_kernel<<<a.nblk, IB_STITCH_THREADS, stitch_smem, st>>>(a.d_len, R, kmax, a.d_walk, a.d_woff, a.d_orbit));
     BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_walk_emit_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_out));
     BRA_CUDA_TRY(cudaGetLastError());

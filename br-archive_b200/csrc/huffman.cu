@@ -253,6 +253,7 @@ bool huf_encode_batch(const HufEncArgs& a, cudaStream_t st)
 #define HD_ROW_WORDS (HD_SUB_BITS / 32)         // 32 words per subsequence
 #define HD_SMEM_WORDS (HD_SEQ_BYTES / 4 + HD_ROW_WORDS)  // + one row of look-ahead for codes crossing the sequence end
 #define HD_LUT_BITS 11
+#define HD_WARMUP_BITS 96u
 
 // per-block decode tables, built once per block by one thread
 __global__ void __launch_bounds__(32) huf_dec_tables_kernel(const uint8_t* __restrict__ hdr, bra_huf_dec_t* __restrict__ tabs, uint32_t* __restrict__ err)
@@ -409,15 +410,30 @@ __global__ void __launch_bounds__(HD_THREADS)
     const uint32_t k        = threadIdx.x;
     const uint64_t sub_idx  = sidx * HD_THREADS + k;
     const uint32_t data_end = min((uint32_t) HD_SEQ_BITS + 64u, (c - seq * HD_SEQ_BYTES) * 8u);  // relative bit where the payload ends
-    // current guess for this subsequence's first codeword
-    S.start[k] = first_run ? k * HD_SUB_BITS : k * HD_SUB_BITS + sub_start[sub_idx];
+    __syncthreads();
+    hd_build_lut(S);
+    __syncthreads();
+    // current guess for this subsequence's first codeword. First run: decode a short warm-up
+    // stretch ahead of the subsequence -- a prefix code re-synchronises within a few codewords on
+    // compressible data, so the first boundary crossed is usually already the true one.
+    {
+        uint32_t guess = k * HD_SUB_BITS;
+        if (!first_run)
+            guess += sub_start[sub_idx];
+        else if (k != 0)
+        {
+            uint32_t cnt_unused;
+            bool     dead;
+            const uint32_t g = hd_walk(S, k * HD_SUB_BITS - HD_WARMUP_BITS, k * HD_SUB_BITS, data_end, &cnt_unused, &dead);
+            if (!dead && g >= k * HD_SUB_BITS && g < k * HD_SUB_BITS + 32u) guess = g;
+        }
+        S.start[k] = guess;
+    }
     if (k == 0)
     {
         S.start[0]          = entry;
         S.start[HD_THREADS] = first_run ? HD_SEQ_BITS : HD_SEQ_BITS + seq_exit[sidx];
     }
-    __syncthreads();
-    hd_build_lut(S);
     __syncthreads();
 
     uint32_t used  = 0xFFFFFFFFu;  // start value my current (exit, count) were computed from

@@ -326,6 +326,96 @@ __global__ void __launch_bounds__(MTF_WARPS * 32)
     mtf_replay<ENCODE, true>(L, in + off, out + off, m);
 }
 
+// ---- encode apply with the INVERSE list ------------------------------------------------------------
+// For encoding only the rank of the incoming symbol matters, so the warp keeps pos[symbol] instead of
+// the list: lane l holds the positions of symbols 8l..8l+7 as bytes of (plo, phi). One symbol costs a
+// shuffle (read pos[x]), a branch-free SIMD-within-register "+1 to every position below pos[x]" on
+// the lane's eight bytes, and a byte clear -- independent of the rank, which is what uniform random
+// input (mean rank ~128) needs.
+__device__ __forceinline__ uint32_t swar_inc_below(uint32_t a, uint32_t pl, bool p_high)
+{
+    // per byte: a += (a < p), p replicated; pl = low 7 bits of p replicated, p_high = bit 7 of p
+    const uint32_t t  = ((a & 0x7F7F7F7Fu) | 0x80808080u) - pl;  // bit 7 of each byte: low7(a) >= low7(p)
+    const uint32_t lt = p_high ? ~(a & t) : ~(a | t);            // bit 7: a < p
+    return a + ((lt & 0x80808080u) >> 7);
+}
+
+__global__ void __launch_bounds__(MTF_WARPS * 32)
+    mtf_enc_apply_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t stride, const uint32_t* __restrict__ len, uint32_t segs,
+                         const uint8_t* __restrict__ state)
+{
+    __shared__ __align__(8) uint8_t s_pos[MTF_WARPS][256];
+    const uint32_t b = blockIdx.y, w = warp_id(), lane = lane_id();
+    const uint32_t seg = blockIdx.x * MTF_WARPS + w;
+    const uint32_t n   = len[b];
+    if ((uint64_t) seg * MTF_SEG >= n) return;  // whole warps leave; only warp-level syncs below
+    const uint32_t m   = min((uint32_t) MTF_SEG, n - seg * MTF_SEG);
+    const uint64_t off = (uint64_t) b * stride + (uint64_t) seg * MTF_SEG;
+    const uint8_t* ip  = in + off;
+    uint8_t*       op  = out + off;
+
+    // invert the entry list: pos[list[j]] = j
+    const uint2 ent = reinterpret_cast<const uint2*>(state + ((uint64_t) b * segs + seg) * 256)[lane];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        s_pos[w][(ent.x >> (8 * k)) & 0xFFu] = (uint8_t) (lane * 8 + k);
+        s_pos[w][(ent.y >> (8 * k)) & 0xFFu] = (uint8_t) (lane * 8 + 4 + k);
+    }
+    __syncwarp();
+    const uint2 pv  = reinterpret_cast<const uint2*>(s_pos[w])[lane];
+    uint32_t    plo = pv.x, phi = pv.y;
+    uint32_t    front = __shfl_sync(BRA_FULL, ent.x, 0) & 0xFFu;  // symbol at position 0
+
+    for (uint32_t base = 0; base < m; base += 128)
+    {
+        const uint32_t cnt = min(128u, m - base);
+        uint32_t       wrd = 0;
+        if (base + lane * 4 + 4 <= m)
+            wrd = *reinterpret_cast<const uint32_t*>(ip + base + lane * 4);
+        else
+            for (uint32_t k = 0; k < 4; ++k)
+                if (base + lane * 4 + k < m) wrd |= (uint32_t) ip[base + lane * 4 + k] << (8 * k);
+        uint32_t       myow   = 0;
+        const uint32_t nwords = (cnt + 3) >> 2;
+        for (uint32_t wi = 0; wi < nwords; ++wi)
+        {
+            const uint32_t wv   = __shfl_sync(BRA_FULL, wrd, wi);
+            const uint32_t nsym = min(4u, cnt - wi * 4);
+            uint32_t       ow   = 0;
+            if (!(nsym == 4 && wv == front * 0x01010101u))
+            {
+                for (uint32_t k = 0; k < nsym; ++k)
+                {
+                    const uint32_t x = (wv >> (k * 8)) & 0xFFu;
+                    if (x == front) continue;  // rank 0, list unchanged
+                    const uint32_t sh = (x & 3u) * 8;
+                    const uint32_t p  = (__shfl_sync(BRA_FULL, (x & 4u) ? phi : plo, x >> 3) >> sh) & 0xFFu;
+                    const uint32_t pl = (p & 0x7Fu) * 0x01010101u;
+                    const bool     ph = (p & 0x80u) != 0;
+                    plo = swar_inc_below(plo, pl, ph);
+                    phi = swar_inc_below(phi, pl, ph);
+                    if (lane == (x >> 3))
+                    {
+                        if (x & 4u)
+                            phi &= ~(0xFFu << sh);
+                        else
+                            plo &= ~(0xFFu << sh);
+                    }
+                    front = x;
+                    ow |= p << (k * 8);
+                }
+            }
+            if (lane == wi) myow = ow;
+        }
+        if (base + lane * 4 + 4 <= m)
+            *reinterpret_cast<uint32_t*>(op + base + lane * 4) = myow;
+        else
+            for (uint32_t k = 0; k < 4; ++k)
+                if (base + lane * 4 + k < m) op[base + lane * 4 + k] = (myow >> (8 * k)) & 0xFFu;
+    }
+}
+
 uint32_t mtf_segments(uint32_t max_n) { return bra_div_up(max_n, MTF_SEG); }
 
 bool mtf_encode_batch(const uint8_t* d_in, uint8_t* d_out, uint64_t stride, const uint32_t* d_len, uint32_t max_n, uint32_t nblk,
@@ -336,7 +426,7 @@ bool mtf_encode_batch(const uint8_t* d_in, uint8_t* d_out, uint64_t stride, cons
     const dim3     grid(bra_div_up(segs, MTF_WARPS), nblk);
     BRA_LAUNCH(P_MTF_SUMMARY, st, mtf_enc_summary_kernel<<<grid, MTF_WARPS * 32, 0, st>>>(d_in, stride, d_len, segs, d_summ, d_scnt));
     BRA_LAUNCH(P_MTF_SCAN, st, mtf_scan_kernel<true><<<nblk, 32, 0, st>>>(d_summ, d_scnt, d_len, segs, d_state));
-    BRA_LAUNCH(P_MTF_APPLY, st, mtf_apply_kernel<true><<<grid, MTF_WARPS * 32, 0, st>>>(d_in, d_out, stride, d_len, segs, d_state));
+    BRA_LAUNCH(P_MTF_APPLY, st, mtf_enc_apply_kernel<<<grid, MTF_WARPS * 32, 0, st>>>(d_in, d_out, stride, d_len, segs, d_state));
     BRA_CUDA_TRY(cudaGetLastError());
     return true;
 }
