@@ -39,8 +39,8 @@ bool crc_headers(const uint8_t* d_hdr, uint32_t item_bytes, uint32_t nitems, uin
 // ---- sort.cu ------------------------------------------------------------------------------
 size_t radix_hist_bytes(uint32_t max_len, uint32_t nblk);
 bool   radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t stride,
-                      const uint32_t* d_len, const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t bits, uint32_t* d_hist,
-                      cudaStream_t st);
+                      const uint32_t* d_len, const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t bits, bool hist_ready,
+                      uint32_t* d_hist, cudaStream_t st);
 bool   radix_pass_u8_index_packed(const uint8_t* keys, uint32_t* packed_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len,
                                   uint32_t nblk, uint32_t* d_hist, cudaStream_t st);
 bool   radix_pass_u8_index(const uint8_t* keys, uint32_t* vals_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len, uint32_t nblk,
@@ -58,7 +58,7 @@ struct BwtFwdArgs
     uint32_t*       d_primary;
     // workspace (u32 arrays are nblk*stride elements)
     uint32_t *d_keyA, *d_keyB, *d_valA, *d_valB, *d_rankA, *d_rankB;
-    uint8_t*  d_flags;    // nblk*stride bytes
+    uint8_t * d_flags, *d_flags2;  // nblk*stride bytes each (head flags, double buffered across rounds)
     uint32_t* d_hist;     // radix_hist_bytes(max_n, nblk)
     int*      d_tile_last;  // nblk * ceil(max_n/4096)
     uint32_t *d_period, *d_ngroups, *d_notdone;

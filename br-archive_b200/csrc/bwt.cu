@@ -97,12 +97,20 @@ __global__ void bwt_period_select_kernel(const uint32_t* __restrict__ len, const
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t* __restrict__ in, uint64_t stride,
                                                                    const uint32_t* __restrict__ period, uint32_t* __restrict__ keys,
-                                                                   uint32_t* __restrict__ vals)
+                                                                   uint32_t* __restrict__ vals, uint32_t tiles, uint32_t* __restrict__ hist)
 {
+    __shared__ uint32_t sh[256];
     const uint32_t b = blockIdx.y;
     const uint32_t p = period[b];
     const uint32_t tile0 = blockIdx.x * EW_TILE;
-    if (tile0 >= p) return;
+    uint32_t*      hout  = hist + ((uint64_t) b * 256) * tiles + blockIdx.x;  // histogram of the first radix pass (shift 0)
+    if (tile0 >= p)
+    {
+        hout[(uint64_t) threadIdx.x * tiles] = 0;
+        return;
+    }
+    sh[threadIdx.x] = 0;
+    __syncthreads();
     const uint8_t* T    = in + (uint64_t) b * stride;
     const uint64_t base = (uint64_t) b * stride;
     const uint32_t tend = min(p, tile0 + EW_TILE);
@@ -118,7 +126,10 @@ __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t
         }
         keys[base + j] = key;
         vals[base + j] = j;
+        atomicAdd(&sh[key & 0xFFu], 1u);
     }
+    __syncthreads();
+    hout[(uint64_t) threadIdx.x * tiles] = sh[threadIdx.x];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -126,13 +137,15 @@ __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t
 // ------------------------------------------------------------------------------------------------
 // Pass A: head flag per sorted slot j (1 byte), last head of each tile, group count per block.
 //   MODE 0: head <=> sorted key differs from its left neighbour          (after the 4-byte sort)
-//   MODE 1: head <=> (rank[SA[j]], rank[SA[j]+h]) differs from the left   (doubling round)
-//           skeys[j] already equals rank[SA[j]] (it was the sort key).
+//   MODE 1: doubling round. The stable re-bucketing keeps every old group in its slot range, so old
+//           heads stay heads and a slot inside an old group becomes a head iff rank[SA[j]+h] differs
+//           from its left neighbour's. Slots that already were singleton groups are settled: they
+//           need no gather at all (that is most of the block in the late rounds).
 template <int MODE>
 __global__ void __launch_bounds__(EW_THREADS)
     bwt_heads_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ sa, const uint32_t* __restrict__ rank, uint32_t h,
-                     uint64_t stride, const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, uint8_t* __restrict__ flags,
-                     int* __restrict__ tile_last, uint32_t tiles, uint32_t* __restrict__ ngroups)
+                     uint64_t stride, const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, const uint8_t* __restrict__ flags_old,
+                     uint8_t* __restrict__ flags, int* __restrict__ tile_last, uint32_t tiles, uint32_t* __restrict__ ngroups)
 {
     __shared__ int      s_last[8];
     __shared__ uint32_t s_cnt[8];
@@ -150,38 +163,66 @@ __global__ void __launch_bounds__(EW_THREADS)
     if (j0 < p)
     {
         const uint32_t m = min(16u, p - j0);
-        uint32_t       prevk = 0, prevg = 0;
-        if (j0 > 0)
+        uint32_t       fl[4] = {0, 0, 0, 0};
+        if (MODE == 0)
         {
-            prevk = skeys[base + j0 - 1];
-            if (MODE == 1)
+            uint32_t prevk = j0 > 0 ? skeys[base + j0 - 1] : 0u;
+            for (uint32_t i = 0; i < m; ++i)
+            {
+                const uint32_t j = j0 + i;
+                const uint32_t k = skeys[base + j];
+                if (j == 0 || k != prevk)
+                {
+                    fl[i >> 2] |= 1u << ((i & 3) * 8);
+                    last = (int) j;
+                    ++cnt;
+                }
+                prevk = k;
+            }
+        }
+        else
+        {
+            // old flags of my 16 slots + the one after (end of block counts as a head)
+            uint32_t oldmask = 0;
+            if (m == 16)
+            {
+                const uint4    v    = *reinterpret_cast<const uint4*>(flags_old + base + j0);
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 16; ++i)
+                    if ((w[i >> 2] >> ((i & 3) * 8)) & 0xFFu) oldmask |= 1u << i;
+            }
+            else
+                for (uint32_t i = 0; i < m; ++i)
+                    if (flags_old[base + j0 + i]) oldmask |= 1u << i;
+            if (j0 + m >= p || flags_old[base + j0 + m]) oldmask |= 1u << m;
+            uint32_t prevg = 0;
+            if (!(oldmask & 1u))  // slot j0 continues the old group of slot j0-1: need that neighbour's second key
             {
                 uint32_t x = sa[base + j0 - 1] + hm;
                 if (x >= p) x -= p;
                 prevg = rank[base + x];
             }
-        }
-        uint32_t fl[4] = {0, 0, 0, 0};
-        for (uint32_t i = 0; i < m; ++i)
-        {
-            const uint32_t j = j0 + i;
-            const uint32_t k = skeys[base + j];
-            uint32_t       g = 0;
-            if (MODE == 1)
+            for (uint32_t i = 0; i < m; ++i)
             {
-                uint32_t x = sa[base + j] + hm;
-                if (x >= p) x -= p;
-                g = rank[base + x];
+                const uint32_t j       = j0 + i;
+                const bool     oldhead = (oldmask >> i) & 1u, nexthead = (oldmask >> (i + 1)) & 1u;
+                bool           head    = true;
+                if (!(oldhead && nexthead))
+                {
+                    uint32_t x = sa[base + j] + hm;
+                    if (x >= p) x -= p;
+                    const uint32_t g = rank[base + x];
+                    head             = oldhead || g != prevg;
+                    prevg            = g;
+                }
+                if (head)
+                {
+                    fl[i >> 2] |= 1u << ((i & 3) * 8);
+                    last = (int) j;
+                    ++cnt;
+                }
             }
-            const bool head = (j == 0) || k != prevk || (MODE == 1 && g != prevg);
-            if (head)
-            {
-                fl[i >> 2] |= 1u << ((i & 3) * 8);
-                last = (int) j;
-                ++cnt;
-            }
-            prevk = k;
-            prevg = g;
         }
         if (m == 16)
             *reinterpret_cast<uint4*>(flags + base + j0) = make_uint4(fl[0], fl[1], fl[2], fl[3]);
@@ -214,10 +255,12 @@ __global__ void __launch_bounds__(EW_THREADS)
     }
 }
 
-// Pass B: rank_out[SA[j]] = index of the head of j's group.
+// Pass B: rank[SA[j]] = index of the head of j's group, in place. Slots that were singleton groups
+// before this round (flags_old) keep their rank and are not touched.
 __global__ void __launch_bounds__(EW_THREADS)
-    bwt_ranks_kernel(const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags, uint64_t stride, const uint32_t* __restrict__ period,
-                     const uint8_t* __restrict__ skip, const int* __restrict__ tile_last, uint32_t tiles, uint32_t* __restrict__ rank_out)
+    bwt_ranks_kernel(const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ flags_old, uint64_t stride,
+                     const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, const int* __restrict__ tile_last, uint32_t tiles,
+                     uint32_t* __restrict__ rank_out)
 {
     __shared__ int red[33];
     const uint32_t b = blockIdx.y;
@@ -240,18 +283,24 @@ __global__ void __launch_bounds__(EW_THREADS)
 
     const uint32_t j0 = tile0 + threadIdx.x * 16;
     const uint32_t m  = j0 < p ? min(16u, p - j0) : 0u;
-    uint8_t        f[16];
+    uint32_t       newmask = 0, oldmask = 0;
     int            mylast = -1;
     for (uint32_t i = 0; i < m; ++i)
     {
-        f[i] = flags[base + j0 + i];
-        if (f[i]) mylast = (int) (j0 + i);
+        if (flags[base + j0 + i])
+        {
+            newmask |= 1u << i;
+            mylast = (int) (j0 + i);
+        }
+        if (flags_old && flags_old[base + j0 + i]) oldmask |= 1u << i;
     }
+    if (flags_old && m && (j0 + m >= p || flags_old[base + j0 + m])) oldmask |= 1u << m;
     int run = max(block_excl_max(mylast, -1, red), carry);
     for (uint32_t i = 0; i < m; ++i)
     {
-        if (f[i]) run = (int) (j0 + i);
-        rank_out[base + sa[base + j0 + i]] = (uint32_t) run;
+        if (newmask & (1u << i)) run = (int) (j0 + i);
+        const bool settled = ((oldmask >> i) & 3u) == 3u;  // was a singleton group already: rank unchanged
+        if (!settled) rank_out[base + sa[base + j0 + i]] = (uint32_t) run;
     }
 }
 
@@ -277,17 +326,27 @@ __global__ void bwt_check_done_kernel(const uint32_t* __restrict__ period, uint3
     ngroups[b] = 0;
 }
 
-// doubling round, step 1: keys/vals in current-order traversal
+// doubling round, step 1: keys/vals in current-order traversal. The tile is the radix sort's tile, so the
+// digit histogram of the first pass (low 8 bits of the key) is produced here and that pass skips its
+// own histogram kernel.
 __global__ void __launch_bounds__(EW_THREADS)
     bwt_dbl_prepare_kernel(const uint32_t* __restrict__ sa, const uint32_t* __restrict__ rank, uint32_t h, uint64_t stride,
                            const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, uint32_t* __restrict__ keys,
-                           uint32_t* __restrict__ vals)
+                           uint32_t* __restrict__ vals, uint32_t tiles, uint32_t* __restrict__ hist)
 {
-    const uint32_t b = blockIdx.y;
+    __shared__ uint32_t sh[256];
+    const uint32_t      b = blockIdx.y;
     if (skip[b]) return;
     const uint32_t p     = period[b];
     const uint32_t tile0 = blockIdx.x * EW_TILE;
-    if (tile0 >= p) return;
+    uint32_t*      hout  = hist + ((uint64_t) b * 256) * tiles + blockIdx.x;
+    if (tile0 >= p)
+    {
+        hout[(uint64_t) threadIdx.x * tiles] = 0;
+        return;
+    }
+    sh[threadIdx.x] = 0;
+    __syncthreads();
     const uint64_t base = (uint64_t) b * stride;
     const uint32_t tend = min(p, tile0 + EW_TILE);
     const uint32_t hm   = h % p;
@@ -295,9 +354,13 @@ __global__ void __launch_bounds__(EW_THREADS)
     {
         const uint32_t s = sa[base + j];
         const uint32_t v = s >= hm ? s - hm : s + p - hm;
+        const uint32_t k = rank[base + v];
         vals[base + j]   = v;
-        keys[base + j]   = rank[base + v];
+        keys[base + j]   = k;
+        atomicAdd(&sh[k & 0xFFu], 1u);
     }
+    __syncthreads();
+    hout[(uint64_t) threadIdx.x * tiles] = sh[threadIdx.x];
 }
 
 // 4. last column + primary index
@@ -394,17 +457,18 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
 
     // ---- 4-byte radix sort
     uint32_t *kA = a.d_keyA, *kB = a.d_keyB, *vA = a.d_valA, *vB = a.d_valB;
-    BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, kA, vA));
+    BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, kA, vA, tiles, a.d_hist));
     for (uint32_t shift = 0; shift < 32; shift += 8)
     {
-        if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, shift, 8, a.d_hist, st)) return false;
+        if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, shift, 8, /*hist_ready=*/shift == 0, a.d_hist, st)) return false;
         std::swap(kA, kB);
         std::swap(vA, vB);
     }
-    uint32_t *rk = a.d_rankA, *rk2 = a.d_rankB;
-    BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<0><<<grid, EW_THREADS, 0, st>>>(kA, vA, nullptr, 0, a.stride, a.d_period, a.d_done, a.d_flags, a.d_tile_last, tiles,
+    uint32_t* rk = a.d_rankA;  // ranks are updated in place
+    uint8_t * fcur = a.d_flags, *fnext = a.d_flags2;
+    BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<0><<<grid, EW_THREADS, 0, st>>>(kA, vA, nullptr, 0, a.stride, a.d_period, a.d_done, nullptr, fcur, a.d_tile_last, tiles,
                                                       a.d_ngroups));
-    BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, a.d_flags, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk));
+    BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fcur, nullptr, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk));
 
     uint32_t h = 4, rounds = 0;
     uint32_t key_bits = 1;
@@ -423,21 +487,19 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             bra_b200_log_error("bwt: prefix doubling did not converge (h=%u, max_n=%u, %u blocks left)", h, max_n, notdone);
             return false;
         }
-        BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, h, a.stride, a.d_period, a.d_done, kB, vB));
+        BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, h, a.stride, a.d_period, a.d_done, kB, vB, tiles, a.d_hist));
         std::swap(kA, kB);
         std::swap(vA, vB);
-        // ranks below 2^20 sort in two 10-bit passes, smaller or larger blocks in 8-bit passes
-        const uint32_t digit = (key_bits > 16 && key_bits <= 20) ? 10u : 8u;
-        for (uint32_t shift = 0; shift < key_bits; shift += digit)
+        for (uint32_t shift = 0; shift < key_bits; shift += 8)
         {
-            if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, shift, digit, a.d_hist, st)) return false;
+            if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, shift, 8, /*hist_ready=*/shift == 0, a.d_hist, st)) return false;
             std::swap(kA, kB);
             std::swap(vA, vB);
         }
-        BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(kA, vA, rk, h, a.stride, a.d_period, a.d_done, a.d_flags, a.d_tile_last, tiles,
+        BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(nullptr, vA, rk, h, a.stride, a.d_period, a.d_done, fcur, fnext, a.d_tile_last, tiles,
                                                           a.d_ngroups));
-        BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, a.d_flags, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk2));
-        std::swap(rk, rk2);
+        BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk));
+        std::swap(fcur, fnext);
         h *= 2;
         ++rounds;
     }

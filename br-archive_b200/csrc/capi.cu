@@ -158,7 +158,7 @@ extern "C" bool bra_bwt_encode2(const uint8_t* buf, const bra_bwt_index_t n, bra
     const uint64_t S     = pad16(n);
     const uint64_t tiles = bra_div_up(S, 4096);
     Bump           B;
-    const uint64_t o_in = B.take<uint8_t>(S), o_out = B.take<uint8_t>(S), o_flags = B.take<uint8_t>(S);
+    const uint64_t o_in = B.take<uint8_t>(S), o_out = B.take<uint8_t>(S), o_flags = B.take<uint8_t>(S), o_flags2 = B.take<uint8_t>(S);
     uint64_t       o_u32[6];
     for (auto& o : o_u32) o = B.take<uint32_t>(S);
     const uint64_t o_hist = B.take<uint8_t>(radix_hist_bytes((uint32_t) S, 1)), o_tl = B.take<int>(tiles);
@@ -172,7 +172,7 @@ extern "C" bool bra_bwt_encode2(const uint8_t* buf, const bra_bwt_index_t n, bra
     a.d_primary = sm + 1;
     a.d_keyA = at<uint32_t>(o_u32[0]); a.d_keyB = at<uint32_t>(o_u32[1]); a.d_valA = at<uint32_t>(o_u32[2]); a.d_valB = at<uint32_t>(o_u32[3]);
     a.d_rankA = at<uint32_t>(o_u32[4]); a.d_rankB = at<uint32_t>(o_u32[5]);
-    a.d_flags = at<uint8_t>(o_flags); a.d_hist = at<uint32_t>(o_hist); a.d_tile_last = at<int>(o_tl);
+    a.d_flags = at<uint8_t>(o_flags); a.d_flags2 = at<uint8_t>(o_flags2); a.d_hist = at<uint32_t>(o_hist); a.d_tile_last = at<int>(o_tl);
     a.d_period = sm + 2; a.d_ngroups = sm + 3; a.d_notdone = sm + 4; a.d_done = at<uint8_t>(o_done);
     a.d_div_vals = at<uint32_t>(o_div); a.d_div_off = sm + 5; a.d_div_cnt = sm + 6; a.div_cap = 4096; a.d_bad = at<uint8_t>(o_bad);
     a.bad_stride = 1024;

@@ -60,7 +60,7 @@ struct Arena
 // workspace requirement of one batch, by dry-running the carve
 struct EncWs
 {
-    uint8_t * L, *M, *R, *flags, *bad, *done, *summ, *state;
+    uint8_t * L, *M, *R, *flags, *flags2, *bad, *done, *summ, *state;
     uint32_t *keyA, *keyB, *valA, *valB, *rankA, *rankB, *hist, *len, *primary, *period, *ngroups, *notdone, *div_vals, *div_off, *div_cnt;
     uint32_t *rlen, *clen, *rhist, *codes, *ok, *t_bits, *t_cnt;
     int *     tile_last, *t_first_head, *t_last_head, *t_first_nl, *t_last_nl;
@@ -84,7 +84,7 @@ static void carve_enc(Arena& A, uint32_t S, uint32_t nb, EncWs& w)
     const uint64_t N = (uint64_t) nb * S, RS = rle_stride_for(S);
     w.keyA = A.take<uint32_t>(N); w.keyB = A.take<uint32_t>(N); w.valA = A.take<uint32_t>(N); w.valB = A.take<uint32_t>(N);
     w.rankA = A.take<uint32_t>(N); w.rankB = A.take<uint32_t>(N);
-    w.L = A.take<uint8_t>(N); w.M = A.take<uint8_t>(N); w.flags = A.take<uint8_t>(N);
+    w.L = A.take<uint8_t>(N); w.M = A.take<uint8_t>(N); w.flags = A.take<uint8_t>(N); w.flags2 = A.take<uint8_t>(N);
     w.R = A.take<uint8_t>((uint64_t) nb * RS);
     w.hist = A.take<uint32_t>(radix_hist_bytes(S, nb) / 4);
     const uint64_t tiles = bra_div_up(S, 4096);
@@ -299,7 +299,7 @@ bool encode_batch(bra_b200_ctx* c, const uint8_t* d_in, uint32_t nb, uint32_t la
     ba.d_in = d_in; ba.d_out = w.L; ba.stride = S; ba.d_len = w.len; ba.h_len = h_len.data(); ba.max_n = S; ba.nblk = nb;
     ba.d_primary = w.primary;
     ba.d_keyA = w.keyA; ba.d_keyB = w.keyB; ba.d_valA = w.valA; ba.d_valB = w.valB; ba.d_rankA = w.rankA; ba.d_rankB = w.rankB;
-    ba.d_flags = w.flags; ba.d_hist = w.hist; ba.d_tile_last = w.tile_last;
+    ba.d_flags = w.flags; ba.d_flags2 = w.flags2; ba.d_hist = w.hist; ba.d_tile_last = w.tile_last;
     ba.d_period = w.period; ba.d_ngroups = w.ngroups; ba.d_notdone = w.notdone; ba.d_done = w.done;
     ba.d_div_vals = w.div_vals; ba.d_div_off = w.div_off; ba.d_div_cnt = w.div_cnt; ba.div_cap = BRA_DIV_CAP;
     ba.d_bad = w.bad; ba.bad_stride = BRA_BAD_STRIDE;

@@ -52,7 +52,16 @@ __global__ void __launch_bounds__(RS_THREADS) rs_hist_kernel(const KeyT* __restr
     __syncthreads();
     const KeyT*    k  = keys + (uint64_t) b * stride + tile0;
     const uint32_t tn = min((uint32_t) RS_TILE, n - tile0);
-    for (uint32_t i = threadIdx.x; i < tn; i += RS_THREADS) atomicAdd(&h[rs_digit<BITS>(k[i], shift)], 1u);
+    KeyT           kv[RS_ITEMS];  // all loads in flight before the first shared-memory atomic
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+    {
+        const uint32_t i = threadIdx.x + r * RS_THREADS;
+        kv[r]            = i < tn ? k[i] : (KeyT) 0;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+        if (threadIdx.x + r * RS_THREADS < tn) atomicAdd(&h[rs_digit<BITS>(kv[r], shift)], 1u);
     __syncthreads();
     for (uint32_t d = threadIdx.x; d < RADIX; d += RS_THREADS) out[(uint64_t) d * tiles] = h[d];
 }
@@ -222,7 +231,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4)
 
 template <int BITS, typename KeyT, bool IMPLICIT, int OUT_MODE>
 static bool radix_pass_t(const KeyT* keys, const uint32_t* vals, KeyT* keys_out, uint32_t* vals_out, uint64_t stride, const uint32_t* d_len,
-                         const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t* d_hist, cudaStream_t st)
+                         const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, bool hist_ready, uint32_t* d_hist, cudaStream_t st)
 {
     if (nblk == 0 || max_len == 0) return true;
     const uint32_t tiles = bra_div_up(max_len, RS_TILE);
@@ -230,7 +239,8 @@ static bool radix_pass_t(const KeyT* keys, const uint32_t* vals, KeyT* keys_out,
     // per-device attribute: set it on every call (cheap) so that multi-GPU processes are covered
     BRA_CUDA_TRY(cudaFuncSetAttribute(rs_scatter_kernel<BITS, KeyT, IMPLICIT, OUT_MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
     const int scatter_id = sizeof(KeyT) == 1 ? P_RS_SCATTER_U8 : P_RS_SCATTER;
-    BRA_LAUNCH(P_RS_HIST, st, rs_hist_kernel<BITS, KeyT><<<dim3(tiles, nblk), RS_THREADS, 0, st>>>(keys, stride, d_len, d_skip, shift, tiles, d_hist));
+    if (!hist_ready)  // the producer of the keys may already have filled d_hist for this digit
+        BRA_LAUNCH(P_RS_HIST, st, rs_hist_kernel<BITS, KeyT><<<dim3(tiles, nblk), RS_THREADS, 0, st>>>(keys, stride, d_len, d_skip, shift, tiles, d_hist));
     BRA_LAUNCH(P_RS_SCAN, st, rs_scan_kernel<<<nblk, 1024, 0, st>>>(d_hist, d_skip, tiles, 1u << BITS));
     BRA_LAUNCH(scatter_id, st, rs_scatter_kernel<BITS, KeyT, IMPLICIT, OUT_MODE>
         <<<dim3(tiles, nblk), RS_THREADS, smem, st>>>(keys, vals, keys_out, vals_out, stride, d_len, d_skip, shift, tiles, d_hist));
@@ -243,23 +253,23 @@ size_t radix_hist_bytes(uint32_t max_len, uint32_t nblk) { return (size_t) nblk 
 
 bool radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t stride,
                     const uint32_t* d_len, const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t bits,
-                    uint32_t* d_hist, cudaStream_t st)
+                    bool hist_ready, uint32_t* d_hist, cudaStream_t st)
 {
     if (bits == 10)
-        return radix_pass_t<10, uint32_t, false, 0>(keys, vals, keys_out, vals_out, stride, d_len, d_skip, max_len, nblk, shift, d_hist, st);
-    return radix_pass_t<8, uint32_t, false, 0>(keys, vals, keys_out, vals_out, stride, d_len, d_skip, max_len, nblk, shift, d_hist, st);
+        return radix_pass_t<10, uint32_t, false, 0>(keys, vals, keys_out, vals_out, stride, d_len, d_skip, max_len, nblk, shift, hist_ready, d_hist, st);
+    return radix_pass_t<8, uint32_t, false, 0>(keys, vals, keys_out, vals_out, stride, d_len, d_skip, max_len, nblk, shift, hist_ready, d_hist, st);
 }
 
 bool radix_pass_u8_index_packed(const uint8_t* keys, uint32_t* packed_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len,
                                 uint32_t nblk, uint32_t* d_hist, cudaStream_t st)
 {
-    return radix_pass_t<8, uint8_t, true, 2>(keys, nullptr, nullptr, packed_out, stride, d_len, nullptr, max_len, nblk, 0, d_hist, st);
+    return radix_pass_t<8, uint8_t, true, 2>(keys, nullptr, nullptr, packed_out, stride, d_len, nullptr, max_len, nblk, 0, false, d_hist, st);
 }
 
 bool radix_pass_u8_index(const uint8_t* keys, uint32_t* vals_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len, uint32_t nblk,
                          uint32_t* d_hist, cudaStream_t st)
 {
-    return radix_pass_t<8, uint8_t, true, 1>(keys, nullptr, nullptr, vals_out, stride, d_len, nullptr, max_len, nblk, 0, d_hist, st);
+    return radix_pass_t<8, uint8_t, true, 1>(keys, nullptr, nullptr, vals_out, stride, d_len, nullptr, max_len, nblk, 0, false, d_hist, st);
 }
 
 }  // namespace bra
