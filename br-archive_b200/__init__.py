@@ -144,6 +144,43 @@ def gen_periodic(n: int, pattern: bytes):
     return out
 
 
+# ---------------------------------------------------------------------------------------------
+# multi-GPU host logic: blocks are independent, so ranks take contiguous block ranges and the per-rank
+# CRC chains are folded on the host; no data-path collective exists.
+# ---------------------------------------------------------------------------------------------
+def shard_range(nblk: int, rank: int, world: int):
+    """Contiguous block range [lo, hi) of `rank`; the first nblk % world ranks get one extra block."""
+    base, extra = divmod(nblk, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def chain_bytes(block_lens):
+    """Bytes the per-entry CRC chain covers for these blocks: 268-byte in-memory header + raw block each
+    (reference src/io/lib_bra_io_file_chunks.c:248-249)."""
+    return sum(HDR_BYTES + int(n) for n in block_lens)
+
+
+def fold_crc_chains(parts):
+    """parts: [(crc_chain_of_rank_started_from_0, bytes_covered)] in rank order -> CRC chain of the whole
+    block sequence, via bra_crc32c_combine (host arithmetic, no GPU needed). Lengths above 2^32-1 are
+    folded piecewise because the reference's combine takes a 32-bit length."""
+    L = lib()
+    L.bra_crc32c_combine.restype = C.c_uint32
+    L.bra_crc32c_combine.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32]
+    crc = 0
+    for part_crc, nbytes in parts:
+        if nbytes == 0:
+            continue
+        # advance crc over nbytes zero-effect bytes: combine(crc, 0-chain, len) in pieces, then xor in the part
+        remaining = nbytes
+        while remaining > 0xFFFFFFFF:
+            crc = L.bra_crc32c_combine(crc, 0, 0xFFFFFFFF)
+            remaining -= 0xFFFFFFFF
+        crc = L.bra_crc32c_combine(crc, part_crc, remaining)
+    return int(crc)
+
+
 class Context:
     """One GPU context of the batched path (include/bra_b200.h). Tensors are torch CUDA uint8/int32."""
 

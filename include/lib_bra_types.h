@@ -12,6 +12,16 @@
 
 typedef uint32_t bra_bwt_index_t; /* rotation index / block length; 3 bytes of it reach the disk */
 
+/* Not used by the hot path, but other reference headers that test programs include next to the encoder
+ * headers (src/fs/bra_fs.hpp) expect this header to provide them (reference lib_bra_types.h:10,16-21). */
+typedef uint8_t bra_attr_t;
+typedef enum bra_fs_overwrite_policy_e
+{
+    BRA_OVERWRITE_ASK        = 0,
+    BRA_OVERWRITE_ALWAYS_YES = 1,
+    BRA_OVERWRITE_ALWAYS_NO  = 2,
+} bra_fs_overwrite_policy_e;
+
 #pragma pack(push, 1)
 typedef struct bra_huffman_t
 {

@@ -341,3 +341,25 @@ def test_decode_rejects_corrupt_blocks(pkg, oracle, vocab):
         assert out.cpu().numpy()[:block].tobytes() == data[:block]
     finally:
         ctx.close()
+
+
+# ------------------------------------------------------------------------------------------ the reference's own tests
+def test_reference_unit_test_programs_pass_against_the_dropin(golden, tmp_path):
+    """oracle/_ref/test_bra_encoders and test_bra_crc32c are the reference's own test programs
+    (test/test_bra_encoders.cpp, test/test_bra_crc32c.cpp), compiled from where they lie against
+    libbra_b200.so (oracle/Makefile: ref_tests). They must pass unchanged."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    (tmp_path / "fixtures").mkdir()
+    (tmp_path / "fixtures" / "lorem.txt").write_bytes(H(golden["blocks"]["lorem_txt"]["in"]))  # test_bra_crc32c_combine2 reads it
+    ran = 0
+    for name in ("test_bra_encoders", "test_bra_crc32c"):
+        exe = os.path.join(root, "oracle", "_ref", name)
+        if not os.path.exists(exe):
+            continue
+        r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, (name, r.stdout[-2000:], r.stderr[-2000:])
+        ran += 1
+    if ran == 0:
+        pytest.skip("oracle/_ref test programs not built (needs /root/reference at build time)")
