@@ -276,7 +276,15 @@ def main():
         fam, (fam_launches, fam_ms) = max(prof.items(), key=lambda kv: kv[1][1])
         kernel_ms = sum(ms for _, ms in prof.values())
         elems = min(args.batch, nblk) * block                      # elements one launch of a batch-wide kernel covers
-        alg_bytes = {"radix_scatter": 16 * elems, "radix_hist": 4 * elems, "radix_scatter_u8": 5 * elems}.get(fam)
+        # algorithmic bytes one launch of each batch-wide kernel family moves; payload-sized
+        # kernels use the measured payload / RLE sizes of the batch
+        share = min(args.batch, nblk) / nblk
+        alg_table = {"radix_scatter": 16 * elems, "radix_hist": 4 * elems, "radix_scatter_u8": 5 * elems, "mtf_apply": 2 * elems,
+                     "mtf_summary": elems, "bwt_ranks": 9 * elems, "bwt_heads": 9 * elems, "bwt_prepare": 16 * elems, "bwt_finish": 10 * elems,
+                     "bwt_gather": 6 * elems, "crc32c": elems, "ibwt_walk_len": 4 * elems, "ibwt_walk_emit": 5 * elems,
+                     "huf_dec_sync": c_sum * share, "huf_dec_write": (c_sum + r_sum) * share, "huf_pack": (r_sum + c_sum) * share,
+                     "rle_enc_emit": elems + r_sum * share, "rle_dec_expand": elems + r_sum * share}
+        alg_bytes = alg_table.get(fam)
         roof = {"bound": "hbm", "kernel": fam, "launches": fam_launches, "avg_launch_ms": fam_ms / max(fam_launches, 1),
                 "share_of_kernel_time": fam_ms / kernel_ms if kernel_ms else None, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
                 "traffic": None}

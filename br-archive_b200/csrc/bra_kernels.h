@@ -12,7 +12,7 @@ namespace bra {
 // ---- prof.cu: launch accounting (see include/bra_b200.h, bra_b200_prof_*) ------------------------
 enum ProfId
 {
-    P_CRC, P_RS_HIST, P_RS_SCAN, P_RS_SCATTER, P_RS_SCATTER_U8, P_BWT_PERIOD, P_BWT_KEYS, P_BWT_HEADS, P_BWT_RANKS, P_BWT_PREPARE, P_BWT_GATHER, P_BWT_MISC,
+    P_CRC, P_RS_HIST, P_RS_SCAN, P_RS_SCATTER, P_RS_SCATTER_U8, P_BWT_PERIOD, P_BWT_KEYS, P_BWT_HEADS, P_BWT_RANKS, P_BWT_PREPARE, P_BWT_GATHER, P_BWT_FINISH, P_BWT_MISC,
     P_MTF_SUMMARY, P_MTF_SCAN, P_MTF_APPLY, P_RLE_ENC_HEADS, P_RLE_ENC_LIT, P_RLE_ENC_SIZE, P_RLE_ENC_EMIT, P_RLE_DEC_EXIT, P_RLE_DEC_CHAIN,
     P_RLE_DEC_MARK, P_RLE_DEC_EXPAND, P_HUF_HIST, P_HUF_BUILD, P_HUF_BITS, P_HUF_PACK, P_HUF_DEC_TABLES, P_HUF_DEC_SYNC, P_HUF_DEC_SCAN,
     P_HUF_DEC_WRITE, P_HUF_DEC_TRAILING, P_IBWT_WALK_LEN, P_IBWT_STITCH, P_IBWT_WALK_EMIT, P_GLUE, P_COUNT
@@ -61,8 +61,9 @@ struct BwtFwdArgs
     uint8_t * d_flags, *d_flags2;  // nblk*stride bytes each (head flags, double buffered across rounds)
     uint32_t* d_hist;     // radix_hist_bytes(max_n, nblk)
     int*      d_tile_last;  // nblk * ceil(max_n/4096)
-    uint32_t *d_period, *d_ngroups, *d_notdone;
-    uint8_t*  d_done;
+    uint32_t *d_period, *d_ngroups, *d_notdone /* 2 words */, *d_maxgroup;
+    unsigned long long* d_sumsq;
+    uint8_t * d_done, *d_fin, *d_finskip;
     uint32_t *d_div_vals, *d_div_off, *d_div_cnt;
     uint32_t  div_cap;
     uint8_t*  d_bad;

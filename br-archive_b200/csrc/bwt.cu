@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 __global__ void __launch_bounds__(EW_THREADS)
     bwt_ranks_kernel(const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ flags_old, uint64_t stride,
                      const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, const int* __restrict__ tile_last, uint32_t tiles,
-                     uint32_t* __restrict__ rank_out)
+                     uint32_t* __restrict__ rank_out, uint32_t* __restrict__ maxgroup, unsigned long long* __restrict__ sumsq)
 {
     __shared__ int red[33];
     const uint32_t b = blockIdx.y;
@@ -296,24 +296,62 @@ __global__ void __launch_bounds__(EW_THREADS)
     }
     if (flags_old && m && (j0 + m >= p || flags_old[base + j0 + m])) oldmask |= 1u << m;
     int run = max(block_excl_max(mylast, -1, red), carry);
+    // group statistics for the finisher decision: every head closes the group before it
+    uint32_t           mg = 0;
+    unsigned long long sq = 0;
     for (uint32_t i = 0; i < m; ++i)
     {
-        if (newmask & (1u << i)) run = (int) (j0 + i);
+        if (newmask & (1u << i))
+        {
+            const uint32_t j = j0 + i;
+            if (j > 0)
+            {
+                const uint32_t g = j - (uint32_t) run;
+                mg               = max(mg, g);
+                if (g > 1) sq += (unsigned long long) g * g;
+            }
+            run = (int) j;
+        }
         const bool settled = ((oldmask >> i) & 3u) == 3u;  // was a singleton group already: rank unchanged
         if (!settled) rank_out[base + sa[base + j0 + i]] = (uint32_t) run;
+    }
+    if (m && j0 + m == p)  // the last group of the block ends at p
+    {
+        const uint32_t g = p - (uint32_t) run;
+        mg               = max(mg, g);
+        if (g > 1) sq += (unsigned long long) g * g;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        mg = max(mg, __shfl_xor_sync(BRA_FULL, mg, d));
+        sq += __shfl_xor_sync(BRA_FULL, sq, d);
+    }
+    if (lane_id() == 0 && mg)
+    {
+        atomicMax(&maxgroup[b], mg);
+        if (sq) atomicAdd(&sumsq[b], sq);
     }
 }
 
 // Block state machine kept in done[b]: 0 = still sorting, 1 = order complete this round (its last
 // column is gathered right away from the buffer that currently holds its suffix array, because
 // finished blocks are skipped by later rounds and the ping-pong buffers move on), 2 = finished.
-// *notdone counts the blocks still sorting.
-__global__ void bwt_check_done_kernel(const uint32_t* __restrict__ period, uint32_t* __restrict__ ngroups, uint8_t* __restrict__ done,
-                                      uint32_t* __restrict__ notdone, uint32_t nblk)
+// fin[b]: 0 = finisher not tried, 1 = selected for the finisher now, 2 = tried.
+// stat[0] counts the blocks still sorting, stat[1] those selected for the finisher.
+#define FIN_MAX_GROUP 512u   // longest group a finisher thread will scan
+#define FIN_WORK_PER_ELEM 16 // finisher is used when sum(g^2) <= this * p (bounded extra work)
+#define FIN_DEPTH 64u        // bytes compared beyond the h already known equal
+
+__global__ void bwt_check_done_kernel(const uint32_t* __restrict__ period, const uint32_t* __restrict__ ngroups, uint8_t* __restrict__ done,
+                                      uint8_t* __restrict__ fin, uint8_t* __restrict__ finskip, const uint32_t* __restrict__ maxgroup,
+                                      const unsigned long long* __restrict__ sumsq, uint32_t* __restrict__ stat, uint32_t nblk)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk) return;
     const uint8_t d = done[b];
+    uint8_t       f = fin[b];
+    if (f == 1) f = 2;
     if (d == 1)
         done[b] = 2;
     else if (d == 0)
@@ -321,9 +359,142 @@ __global__ void bwt_check_done_kernel(const uint32_t* __restrict__ period, uint3
         if (ngroups[b] >= period[b])
             done[b] = 1;
         else
-            atomicAdd(notdone, 1u);
+        {
+            atomicAdd(&stat[0], 1u);
+            if (f == 0 && maxgroup[b] <= FIN_MAX_GROUP && sumsq[b] <= (unsigned long long) FIN_WORK_PER_ELEM * period[b])
+            {
+                f = 1;
+                atomicAdd(&stat[1], 1u);
+            }
+        }
     }
-    ngroups[b] = 0;
+    fin[b]     = f;
+    finskip[b] = !(done[b] == 0 && f == 1);
+}
+
+__global__ void bwt_reset_stats_kernel(const uint8_t* __restrict__ skip, uint32_t* __restrict__ ngroups, uint32_t* __restrict__ maxgroup,
+                                       unsigned long long* __restrict__ sumsq, uint32_t nblk)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk || skip[b]) return;
+    ngroups[b]  = 0;
+    maxgroup[b] = 0;
+    sumsq[b]    = 0;
+}
+
+// Finisher: when the remaining groups are small, order each of them by comparing the rotations
+// directly (bytes h .. h+FIN_DEPTH-1; everything before is known equal). Every member counts the
+// members that sort before it, so the kernel is fully parallel. Members still equal after FIN_DEPTH
+// bytes stay one group (in their current order) and go on with prefix doubling.
+__device__ __forceinline__ int rot_cmp_window(const uint8_t* __restrict__ T, uint32_t p, uint32_t a, uint32_t c, uint32_t from)
+{
+    uint32_t ia = (a + from) % p, ic = (c + from) % p;
+    for (uint32_t k = 0; k < FIN_DEPTH; ++k)
+    {
+        const uint8_t x = T[ia], y = T[ic];
+        if (x != y) return x < y ? -1 : 1;
+        if (++ia == p) ia = 0;
+        if (++ic == p) ic = 0;
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+    bwt_finish_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip,
+                      uint32_t h, const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags_old, uint32_t* __restrict__ sa_out,
+                      uint8_t* __restrict__ flags_new, int* __restrict__ tile_last, uint32_t tiles, uint32_t* __restrict__ ngroups)
+{
+    const uint32_t b = blockIdx.y;
+    if (skip[b]) return;
+    const uint32_t p     = period[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= p) return;
+    const uint64_t base = (uint64_t) b * stride;
+    const uint8_t* T    = in + base;
+    const uint8_t* fo   = flags_old + base;
+    const uint32_t tend = min(p, tile0 + EW_TILE);
+    uint32_t       heads = 0;
+    int            best  = -1;  // last head that lands in this tile
+    __shared__ int      s_best[8];
+    __shared__ uint32_t s_heads[8];
+    for (uint32_t j = tile0 + threadIdx.x; j < tend; j += EW_THREADS)
+    {
+        const uint32_t me = sa[base + j];
+        uint32_t       pos = j;
+        bool           head = true;
+        if (!(fo[j] && (j + 1 == p || fo[j + 1])))
+        {
+            uint32_t s = j, e = j + 1;
+            while (!fo[s]) --s;            // slot 0 is always a head
+            while (e < p && !fo[e]) ++e;
+            uint32_t less = 0, tie_before = 0;
+            for (uint32_t m = s; m < e; ++m)
+            {
+                if (m == j) continue;
+                const int c = rot_cmp_window(T, p, me, sa[base + m], h);
+                if (c > 0)
+                    ++less;
+                else if (c == 0 && m < j)
+                {
+                    ++less;
+                    ++tie_before;
+                }
+            }
+            pos  = s + less;
+            head = tie_before == 0;
+        }
+        sa_out[base + pos]    = me;
+        flags_new[base + pos] = head ? 1 : 0;
+        if (head)
+        {
+            ++heads;
+            if (pos >= tile0 && pos < tend)
+                best = max(best, (int) pos);
+            else
+                atomicMax(&tile_last[(uint64_t) b * tiles + pos / EW_TILE], (int) pos);  // member moved across a tile border (rare)
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        heads += __shfl_xor_sync(BRA_FULL, heads, d);
+        best = max(best, __shfl_xor_sync(BRA_FULL, best, d));
+    }
+    if (lane_id() == 0)
+    {
+        s_best[warp_id()]  = best;
+        s_heads[warp_id()] = heads;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int i = 1; i < 8; ++i)
+        {
+            best = max(best, s_best[i]);
+            heads += s_heads[i];
+        }
+        if (best >= 0) atomicMax(&tile_last[(uint64_t) b * tiles + blockIdx.x], best);
+        if (heads) atomicAdd(&ngroups[b], heads);
+    }
+}
+
+// after the finisher: bring the selected blocks' order and flags back into the current buffers
+__global__ void __launch_bounds__(EW_THREADS)
+    bwt_copyback_kernel(uint64_t stride, const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, const uint32_t* __restrict__ sa_src,
+                        uint32_t* __restrict__ sa_dst, const uint8_t* __restrict__ fl_src, uint8_t* __restrict__ fl_dst)
+{
+    const uint32_t b = blockIdx.y;
+    if (skip[b]) return;
+    const uint32_t p     = period[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= p) return;
+    const uint64_t base = (uint64_t) b * stride;
+    const uint32_t tend = min(p, tile0 + EW_TILE);
+    for (uint32_t j = tile0 + threadIdx.x; j < tend; j += EW_THREADS)
+    {
+        sa_dst[base + j] = sa_src[base + j];
+        fl_dst[base + j] = fl_src[base + j];
+    }
 }
 
 // doubling round, step 1: keys/vals in current-order traversal. The tile is the radix sort's tile, so the
@@ -466,27 +637,46 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     }
     uint32_t* rk = a.d_rankA;  // ranks are updated in place
     uint8_t * fcur = a.d_flags, *fnext = a.d_flags2;
+    const dim3 g1(bra_div_up(nblk, 128));
+    BRA_CUDA_TRY(cudaMemsetAsync(a.d_fin, 0, nblk, st));
+    BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_done, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
     BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<0><<<grid, EW_THREADS, 0, st>>>(kA, vA, nullptr, 0, a.stride, a.d_period, a.d_done, nullptr, fcur, a.d_tile_last, tiles,
                                                       a.d_ngroups));
-    BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fcur, nullptr, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk));
+    BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fcur, nullptr, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
+                                                                          a.d_maxgroup, a.d_sumsq));
 
-    uint32_t h = 4, rounds = 0;
+    uint32_t h = 4, rounds = 0, finishes = 0;
     uint32_t key_bits = 1;
     while ((1ull << key_bits) < max_n) ++key_bits;
     for (;;)
     {
-        BRA_CUDA_TRY(cudaMemsetAsync(a.d_notdone, 0, 4, st));
-        BRA_LAUNCH(P_BWT_MISC, st, bwt_check_done_kernel<<<bra_div_up(nblk, 128), 128, 0, st>>>(a.d_period, a.d_ngroups, a.d_done, a.d_notdone, nblk));
+        BRA_CUDA_TRY(cudaMemsetAsync(a.d_notdone, 0, 8, st));
+        BRA_LAUNCH(P_BWT_MISC, st, bwt_check_done_kernel<<<g1, 128, 0, st>>>(a.d_period, a.d_ngroups, a.d_done, a.d_fin, a.d_finskip, a.d_maxgroup, a.d_sumsq,
+                                                                          a.d_notdone, nblk));
         BRA_LAUNCH(P_BWT_GATHER, st, bwt_gather_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, vA, a.stride, a.d_len, a.d_period, a.d_done, a.d_out, a.d_primary));
-        uint32_t notdone = 0;
-        BRA_CUDA_TRY(cudaMemcpyAsync(&notdone, a.d_notdone, 4, cudaMemcpyDeviceToHost, st));
+        uint32_t stat[2] = {0, 0};
+        BRA_CUDA_TRY(cudaMemcpyAsync(stat, a.d_notdone, 8, cudaMemcpyDeviceToHost, st));
         BRA_CUDA_TRY(cudaStreamSynchronize(st));
-        if (notdone == 0) break;
+        if (stat[0] == 0) break;
+        if (stat[1] != 0)
+        {
+            // finisher pass over the selected blocks (everything else keeps its state)
+            BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_finskip, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
+            BRA_CUDA_TRY(cudaMemsetAsync(a.d_tile_last, 0xFF, (size_t) nblk * tiles * sizeof(int), st));
+            BRA_LAUNCH(P_BWT_FINISH, st, bwt_finish_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, a.d_finskip, h, vA, fcur, vB, fnext,
+                                                                                     a.d_tile_last, tiles, a.d_ngroups));
+            BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vB, fnext, fcur, a.stride, a.d_period, a.d_finskip, a.d_tile_last, tiles, rk,
+                                                                                  a.d_maxgroup, a.d_sumsq));
+            BRA_LAUNCH(P_BWT_FINISH, st, bwt_copyback_kernel<<<grid, EW_THREADS, 0, st>>>(a.stride, a.d_period, a.d_finskip, vB, vA, fnext, fcur));
+            ++finishes;
+            continue;
+        }
         if (h >= 2u * max_n + 8u)
         {
-            bra_b200_log_error("bwt: prefix doubling did not converge (h=%u, max_n=%u, %u blocks left)", h, max_n, notdone);
+            bra_b200_log_error("bwt: prefix doubling did not converge (h=%u, max_n=%u, %u blocks left)", h, max_n, stat[0]);
             return false;
         }
+        BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_done, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
         BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, h, a.stride, a.d_period, a.d_done, kB, vB, tiles, a.d_hist));
         std::swap(kA, kB);
         std::swap(vA, vB);
@@ -498,11 +688,13 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         }
         BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(nullptr, vA, rk, h, a.stride, a.d_period, a.d_done, fcur, fnext, a.d_tile_last, tiles,
                                                           a.d_ngroups));
-        BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk));
+        BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
+                                                                              a.d_maxgroup, a.d_sumsq));
         std::swap(fcur, fnext);
         h *= 2;
         ++rounds;
     }
+    (void) finishes;
     if (a.h_rounds) *a.h_rounds = rounds;
     BRA_CUDA_TRY(cudaGetLastError());
     return true;

@@ -173,7 +173,9 @@ extern "C" bool bra_bwt_encode2(const uint8_t* buf, const bra_bwt_index_t n, bra
     a.d_keyA = at<uint32_t>(o_u32[0]); a.d_keyB = at<uint32_t>(o_u32[1]); a.d_valA = at<uint32_t>(o_u32[2]); a.d_valB = at<uint32_t>(o_u32[3]);
     a.d_rankA = at<uint32_t>(o_u32[4]); a.d_rankB = at<uint32_t>(o_u32[5]);
     a.d_flags = at<uint8_t>(o_flags); a.d_flags2 = at<uint8_t>(o_flags2); a.d_hist = at<uint32_t>(o_hist); a.d_tile_last = at<int>(o_tl);
-    a.d_period = sm + 2; a.d_ngroups = sm + 3; a.d_notdone = sm + 4; a.d_done = at<uint8_t>(o_done);
+    a.d_period = sm + 2; a.d_ngroups = sm + 3; a.d_notdone = sm + 8; a.d_done = at<uint8_t>(o_done); a.d_fin = at<uint8_t>(o_done) + 4;
+    a.d_finskip = at<uint8_t>(o_done) + 8; a.d_maxgroup = sm + 4; a.d_sumsq = reinterpret_cast<unsigned long long*>(sm + 12);
+    // sm: [0]len [1]primary [2]period [3]ngroups [4]maxgroup [5]div_off [6]div_cnt [8,9]stat [12,13]sumsq
     a.d_div_vals = at<uint32_t>(o_div); a.d_div_off = sm + 5; a.d_div_cnt = sm + 6; a.div_cap = 4096; a.d_bad = at<uint8_t>(o_bad);
     a.bad_stride = 1024;
     if (!bwt_forward_batch(a, g_st)) return false;
