@@ -141,7 +141,7 @@ def main():
     ap.add_argument("--workload", default="text", choices=["text", "random", "periodic"])
     ap.add_argument("--size-mib", type=int, default=1024)
     ap.add_argument("--block-kib", type=int, default=1024)
-    ap.add_argument("--batch", type=int, default=256, help="blocks per internal batch (bounds device workspace)")
+    ap.add_argument("--batch", type=int, default=1024, help="blocks per internal batch (bounds device workspace)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -9,9 +9,9 @@
 //   scan    : per block, compose the summaries left to right -> the list entering each segment
 //   apply   : replay each segment from its entry list.
 // Replay is one segment per THREAD: each lane owns a 256-byte list in shared memory (stride 65
-// words, so lanes working at the same depth hit different banks) and does what the reference
-// does -- find / shift -- but four list entries per shared-memory word. A warp therefore advances
-// 32 segments at once, and the cost per symbol is (rank/4 + 1) word steps of the slowest lane:
+// eight-byte words, so lanes working at the same depth hit different banks) and does what the reference
+// does -- find / shift -- but eight list entries per shared-memory word. A warp therefore advances
+// 32 segments at once, and the cost per symbol is (rank/8 + 1) word steps of the slowest lane:
 // about one warp instruction per symbol on BWT output (ranks are small), ~20 on uniform random
 // ranks. Traffic: read n + write n (+ 256 B of state per 4 KiB segment, twice). Issue/latency bound.
 #include "bra_common.cuh"
@@ -22,53 +22,53 @@ namespace bra {
 #define MTF_SEG 4096
 #define MTF_WARPS 4          // warps per CTA in the warp-per-segment summary kernel
 #define MTF_LANE_WARPS 4     // warps per CTA in the lane-per-segment replay kernels
-#define MTF_LIST_WORDS 65    // 64 words of list + 1 pad word: lane stride 65 words = conflict-free columns
+#define MTF_LIST_QW 33       // 32 eight-byte words of list + 1 pad: lane stride 33 -> lanes at the same depth use distinct banks
 
 // ---- per-lane list in shared memory -----------------------------------------------------------------
-// W[0..63]: entry k lives in byte (k & 3) of word (k >> 2).
+// Q[0..31]: entry k lives in byte (k & 7) of the 64-bit word (k >> 3).
 
 // decode one rank: returns the symbol at position r and moves it to the front
-__device__ __forceinline__ uint32_t lane_mtf_decode(uint32_t* W, uint32_t r)
+__device__ __forceinline__ uint32_t lane_mtf_decode(uint64_t* Q, uint32_t r)
 {
-    const uint32_t wr = r >> 2, br = r & 3u;
-    uint32_t       cur = W[wr];
-    const uint32_t sym = (cur >> (br * 8)) & 0xFFu;
+    const uint32_t wr = r >> 3, br = r & 7u;
+    uint64_t       cur = Q[wr];
+    const uint32_t sym = (uint32_t) (cur >> (br * 8)) & 0xFFu;
     if (r == 0) return sym;
-    uint32_t below    = wr ? W[wr - 1] : 0u;
-    uint32_t incoming = wr ? (below >> 24) : sym;
-    const uint32_t mask = br == 3 ? 0xFFFFFFFFu : ((1u << ((br + 1) * 8)) - 1u);  // bytes <= br take the shifted image
-    W[wr] = (((cur << 8) | incoming) & mask) | (cur & ~mask);
+    uint64_t       below    = wr ? Q[wr - 1] : 0ull;
+    uint64_t       incoming = wr ? (below >> 56) : (uint64_t) sym;
+    const uint64_t mask     = br == 7 ? ~0ull : ((1ull << ((br + 1) * 8)) - 1ull);  // bytes <= br take the shifted image
+    Q[wr] = (((cur << 8) | incoming) & mask) | (cur & ~mask);
     for (int w = (int) wr - 1; w >= 0; --w)
     {
         cur      = below;
-        below    = w ? W[w - 1] : 0u;
-        incoming = w ? (below >> 24) : sym;
-        W[w]     = (cur << 8) | incoming;
+        below    = w ? Q[w - 1] : 0ull;
+        incoming = w ? (below >> 56) : (uint64_t) sym;
+        Q[w]     = (cur << 8) | incoming;
     }
     return sym;
 }
 
 // encode one symbol: returns its position and moves it to the front (single forward pass)
-__device__ __forceinline__ uint32_t lane_mtf_encode(uint32_t* W, uint32_t x)
+__device__ __forceinline__ uint32_t lane_mtf_encode(uint64_t* Q, uint32_t x)
 {
-    const uint32_t x4 = x * 0x01010101u;
-    uint32_t       carry = x;  // byte entering the next word from below
+    const uint64_t x8    = (uint64_t) x * 0x0101010101010101ull;
+    uint64_t       carry = x;  // byte entering the next word from below
     for (uint32_t w = 0;; ++w)
     {
-        const uint32_t cur = W[w];
-        const uint32_t t   = cur ^ x4;
-        const uint32_t z   = (t - 0x01010101u) & ~t & 0x80808080u;  // lowest set marker = first byte equal to x
+        const uint64_t cur = Q[w];
+        const uint64_t t   = cur ^ x8;
+        const uint64_t z   = (t - 0x0101010101010101ull) & ~t & 0x8080808080808080ull;  // lowest marker = first byte equal to x
         if (z == 0)
         {
-            W[w]  = (cur << 8) | carry;
-            carry = cur >> 24;
+            Q[w]  = (cur << 8) | carry;
+            carry = cur >> 56;
             continue;
         }
-        const uint32_t b = (uint32_t) (__ffs(z) - 1) >> 3;
+        const uint32_t b = (uint32_t) (__ffsll((long long) z) - 1) >> 3;
         if (w == 0 && b == 0) return 0;  // already in front
-        const uint32_t mask = b == 3 ? 0xFFFFFFFFu : ((1u << ((b + 1) * 8)) - 1u);
-        W[w] = (((cur << 8) | carry) & mask) | (cur & ~mask);
-        return w * 4 + b;
+        const uint64_t mask = b == 7 ? ~0ull : ((1ull << ((b + 1) * 8)) - 1ull);
+        Q[w] = (((cur << 8) | carry) & mask) | (cur & ~mask);
+        return w * 8 + b;
     }
 }
 
@@ -79,19 +79,19 @@ __global__ void __launch_bounds__(MTF_LANE_WARPS * 32)
     mtf_lane_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t stride, const uint32_t* __restrict__ len, uint32_t segs,
                     const uint8_t* __restrict__ state_in, uint8_t* __restrict__ summ_out)
 {
-    __shared__ uint32_t s_list[MTF_LANE_WARPS * 32 * MTF_LIST_WORDS];
+    __shared__ uint64_t s_list[MTF_LANE_WARPS * 32 * MTF_LIST_QW];
     const uint32_t b   = blockIdx.y;
     const uint32_t n   = len[b];
     const uint32_t seg = blockIdx.x * (MTF_LANE_WARPS * 32) + threadIdx.x;
     if ((uint64_t) seg * MTF_SEG >= n) return;  // no barriers below: lanes are independent
     const uint32_t m   = min((uint32_t) MTF_SEG, n - seg * MTF_SEG);
     const uint64_t off = (uint64_t) b * stride + (uint64_t) seg * MTF_SEG;
-    uint32_t*      W   = s_list + threadIdx.x * MTF_LIST_WORDS;
+    uint64_t*      W   = s_list + threadIdx.x * MTF_LIST_QW;
 
     if (MODE == 2)
     {
 #pragma unroll 8
-        for (uint32_t w = 0; w < 64; ++w) W[w] = (w * 4) | ((w * 4 + 1) << 8) | ((w * 4 + 2) << 16) | ((w * 4 + 3) << 24);
+        for (uint32_t w = 0; w < 32; ++w) W[w] = 0x0706050403020100ull + (uint64_t) (w * 8) * 0x0101010101010101ull;
     }
     else
     {
@@ -100,10 +100,8 @@ __global__ void __launch_bounds__(MTF_LANE_WARPS * 32)
         for (uint32_t q = 0; q < 16; ++q)
         {
             const uint4 v = st[q];
-            W[q * 4 + 0]  = v.x;
-            W[q * 4 + 1]  = v.y;
-            W[q * 4 + 2]  = v.z;
-            W[q * 4 + 3]  = v.w;
+            W[q * 2 + 0]  = ((uint64_t) v.y << 32) | v.x;
+            W[q * 2 + 1]  = ((uint64_t) v.w << 32) | v.z;
         }
     }
 
@@ -140,7 +138,8 @@ __global__ void __launch_bounds__(MTF_LANE_WARPS * 32)
     {
         uint4* so = reinterpret_cast<uint4*>(summ_out + ((uint64_t) b * segs + seg) * 256);
 #pragma unroll 4
-        for (uint32_t q = 0; q < 16; ++q) so[q] = make_uint4(W[q * 4], W[q * 4 + 1], W[q * 4 + 2], W[q * 4 + 3]);
+        for (uint32_t q = 0; q < 16; ++q)
+            so[q] = make_uint4((uint32_t) W[q * 2], (uint32_t) (W[q * 2] >> 32), (uint32_t) W[q * 2 + 1], (uint32_t) (W[q * 2 + 1] >> 32));
     }
 }
 
