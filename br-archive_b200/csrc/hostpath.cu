@@ -99,6 +99,41 @@ extern "C" uint64_t bra_b200_encode_bound(const bra_b200_ctx_t* c, uint64_t tota
     return nblk * (267 + bra_b200_payload_stride(c));
 }
 
+// RAII bundle of the two copy streams and the events that order them against the compute stream
+namespace {
+struct Pipe
+{
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t  ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    bool         ok = false;
+    Pipe()
+    {
+        ok = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; ++i)
+            ok = cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ev_comp[i], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming) == cudaSuccess;
+    }
+    ~Pipe()
+    {
+        for (int i = 0; i < 2; ++i)
+        {
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+        }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
+    }
+};
+// blocks per pipeline stage: a quarter of the context's batch keeps the kernels wide and hides three quarters of the copies
+inline uint32_t stage_blocks(uint32_t max_batch) { return max_batch >= 64 ? max_batch / 4 : max_batch; }
+}  // namespace
+
+// Three streams: input copies run one stage ahead of the kernels, output copies one stage behind
+// (double-buffered device staging). The kernels' own host syncs (BWT round control) only block the
+// host thread; the copy streams keep moving underneath.
 extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64_t total, uint8_t* out, uint64_t out_cap, uint64_t* out_size,
                                     uint32_t* crc_chain)
 {
@@ -109,61 +144,81 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
     }
     if (cudaSetDevice(ctx_device(c)) != cudaSuccess) return 2;
     const uint32_t S  = bra_b200_block_size(c);
-    const uint32_t MB = bra_b200_max_batch(c);
+    const uint32_t HB = stage_blocks(bra_b200_max_batch(c));
     const uint64_t PS = bra_b200_payload_stride(c);
     const uint64_t nblk_total = (total + S - 1) / S;
+    const uint64_t nstage     = (nblk_total + HB - 1) / HB;
     cudaStream_t   st = ctx_stream(c);
     *out_size         = 0;
+    Pipe P;
+    if (!P.ok) return 2;
 
-    // device staging: input | hdr | payload | stream | offsets | crcs
-    const uint64_t in_b = (uint64_t) MB * S, hdr_b = (uint64_t) MB * 268 + 256, pay_b = (uint64_t) MB * PS, str_b = (uint64_t) MB * (267 + PS),
-                   off_b = ((uint64_t) MB + 1) * 8 + 256, crc_b = (uint64_t) MB * 8 + 256;
-    uint8_t* io = ctx_io_buffer(c, in_b + hdr_b + pay_b + str_b + off_b + crc_b + 4096);
+    // device staging: input x2 | hdr | payload | stream x2 | offsets | crcs
+    auto           up    = [](uint64_t v) { return (v + 255) / 256 * 256; };
+    const uint64_t in_b  = up((uint64_t) HB * S), hdr_b = up((uint64_t) HB * 268), pay_b = up((uint64_t) HB * PS),
+                   str_b = up((uint64_t) HB * (267 + PS)), off_b = up(((uint64_t) HB + 1) * 8), crc_b = up((uint64_t) HB * 8);
+    uint8_t* io = ctx_io_buffer(c, 2 * in_b + hdr_b + pay_b + 2 * str_b + off_b + crc_b + 4096);
     if (!io) return 3;
-    uint8_t*  d_in  = io;
-    uint8_t*  d_hdr = d_in + in_b;
-    uint8_t*  d_pay = d_hdr + hdr_b;
-    uint8_t*  d_str = d_pay + pay_b;
-    uint64_t* d_off = reinterpret_cast<uint64_t*>(d_str + ((str_b + 255) / 256) * 256);
-    uint32_t* d_crc = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_off) + off_b);
-    uint32_t* d_hcrc = d_crc + MB;
+    uint8_t*  d_in[2]  = {io, io + in_b};
+    uint8_t*  d_hdr    = io + 2 * in_b;
+    uint8_t*  d_pay    = d_hdr + hdr_b;
+    uint8_t*  d_str[2] = {d_pay + pay_b, d_pay + pay_b + str_b};
+    uint64_t* d_off    = reinterpret_cast<uint64_t*>(d_str[1] + str_b);
+    uint32_t* d_crc    = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_off) + off_b);
+    uint32_t* d_hcrc   = d_crc + HB;
 
     const bra_gf_pow_t*   pw = crc_host_pow();
-    std::vector<uint32_t> h_crc(2 * (size_t) MB);
+    std::vector<uint32_t> h_crc(2 * (size_t) HB);
     uint32_t              crc = crc_chain ? *crc_chain : 0;
     uint64_t              produced = 0;
-    for (uint64_t b0 = 0; b0 < nblk_total; b0 += MB)
+    auto stage_bytes = [&](uint64_t i) { return std::min<uint64_t>((uint64_t) HB * S, total - i * HB * S); };
+
+    if (cudaMemcpyAsync(d_in[0], in, stage_bytes(0), cudaMemcpyHostToDevice, P.s_in) != cudaSuccess) return 4;
+    cudaEventRecord(P.ev_in[0], P.s_in);
+    for (uint64_t i = 0; i < nstage; ++i)
     {
-        const uint32_t nb    = (uint32_t) std::min<uint64_t>(MB, nblk_total - b0);
-        const uint64_t bytes = std::min<uint64_t>((uint64_t) nb * S, total - b0 * S);
+        const int      slot  = (int) (i & 1);
+        const uint64_t bytes = stage_bytes(i);
+        const uint32_t nb    = (uint32_t) ((bytes + S - 1) / S);
         const uint32_t last  = (uint32_t) (bytes - (uint64_t) (nb - 1) * S);
-        if (cudaMemcpyAsync(d_in, in + b0 * S, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return 4;
-        if (!encode_batch(c, d_in, nb, last, d_hdr, d_pay, d_crc, st)) return 5;
+        if (i + 1 < nstage)
+        {
+            // prefetch the next stage's input; its slot was last read by the kernels of stage i-1
+            if (i >= 1) cudaStreamWaitEvent(P.s_in, P.ev_comp[slot ^ 1], 0);
+            if (cudaMemcpyAsync(d_in[slot ^ 1], in + (i + 1) * HB * S, stage_bytes(i + 1), cudaMemcpyHostToDevice, P.s_in) != cudaSuccess) return 4;
+            cudaEventRecord(P.ev_in[slot ^ 1], P.s_in);
+        }
+        cudaStreamWaitEvent(st, P.ev_in[slot], 0);
+        if (i >= 2) cudaStreamWaitEvent(st, P.ev_out[slot], 0);  // the stream slot is free once stage i-2 has left the device
+        if (!encode_batch(c, d_in[slot], nb, last, d_hdr, d_pay, d_crc, st)) return 5;
         if (!crc_headers(d_hdr, 268, nb, d_hcrc, st)) return 5;
         BRA_LAUNCH(P_GLUE, st, stream_offsets_kernel<<<1, 1024, 0, st>>>(d_hdr, nb, d_off));
         const uint32_t gx = bra_div_up(267 + PS, 4096);
-        BRA_LAUNCH(P_GLUE, st, stream_gather_kernel<<<dim3(gx, nb), 256, 0, st>>>(d_hdr, d_pay, PS, d_off, d_str));
+        BRA_LAUNCH(P_GLUE, st, stream_gather_kernel<<<dim3(gx, nb), 256, 0, st>>>(d_hdr, d_pay, PS, d_off, d_str[slot]));
         uint64_t str_size = 0;
         if (cudaMemcpyAsync(&str_size, d_off + nb, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
         if (cudaMemcpyAsync(h_crc.data(), d_crc, (size_t) nb * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
-        if (cudaMemcpyAsync(h_crc.data() + MB, d_hcrc, (size_t) nb * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+        if (cudaMemcpyAsync(h_crc.data() + HB, d_hcrc, (size_t) nb * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+        cudaEventRecord(P.ev_comp[slot], st);
         if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
         if (produced + str_size > out_cap)
         {
             bra_b200_log_error("bra_b200_encode_host: output buffer too small");
             return 6;
         }
-        if (cudaMemcpyAsync(out + produced, d_str, str_size, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+        cudaStreamWaitEvent(P.s_out, P.ev_comp[slot], 0);
+        if (cudaMemcpyAsync(out + produced, d_str[slot], str_size, cudaMemcpyDeviceToHost, P.s_out) != cudaSuccess) return 4;
+        cudaEventRecord(P.ev_out[slot], P.s_out);
         // CRC chain of reference chunks.c:248-249 while the copy runs
         for (uint32_t b = 0; b < nb; ++b)
         {
             const uint32_t n = (b + 1 == nb) ? last : S;
-            crc = bra_crc_combine(pw, crc, h_crc[MB + b], 268);
+            crc = bra_crc_combine(pw, crc, h_crc[HB + b], 268);
             crc = bra_crc_combine(pw, crc, h_crc[b], n);
         }
-        if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
         produced += str_size;
     }
+    if (cudaStreamSynchronize(P.s_out) != cudaSuccess || cudaStreamSynchronize(P.s_in) != cudaSuccess) return 4;
     *out_size = produced;
     if (crc_chain) *crc_chain = crc;
     return 0;
@@ -179,101 +234,145 @@ extern "C" int bra_b200_decode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
     }
     if (cudaSetDevice(ctx_device(c)) != cudaSuccess) return 2;
     const uint32_t S  = bra_b200_block_size(c);
-    const uint32_t MB = bra_b200_max_batch(c);
+    const uint32_t HB = stage_blocks(bra_b200_max_batch(c));
     const uint64_t PS = bra_b200_payload_stride(c);
     cudaStream_t   st = ctx_stream(c);
     *out_size         = 0;
+    Pipe P;
+    if (!P.ok) return 2;
 
-    const uint64_t str_b = (uint64_t) MB * (267 + PS), hdr_b = (uint64_t) MB * 268 + 256, pay_b = (uint64_t) MB * PS, out_b = (uint64_t) MB * S,
-                   off_b = ((uint64_t) MB + 1) * 8 + 256, misc_b = (uint64_t) MB * 16 + 256;
-    uint8_t* io = ctx_io_buffer(c, str_b + hdr_b + pay_b + 2 * out_b + 2 * off_b + misc_b + 8192);
+    auto           up    = [](uint64_t v) { return (v + 255) / 256 * 256; };
+    const uint64_t str_b = up((uint64_t) HB * (267 + PS)), hdr_b = up((uint64_t) HB * 268), pay_b = up((uint64_t) HB * PS), out_b = up((uint64_t) HB * S),
+                   off_b = up(((uint64_t) HB + 1) * 8), misc_b = up((uint64_t) HB * 16);
+    uint8_t* io = ctx_io_buffer(c, 2 * str_b + hdr_b + pay_b + 3 * out_b + 3 * off_b + misc_b + 8192);
     if (!io) return 3;
-    uint8_t*  d_str  = io;
-    uint8_t*  d_hdr  = d_str + ((str_b + 255) / 256) * 256;
-    uint8_t*  d_pay  = d_hdr + hdr_b;
-    uint8_t*  d_out  = d_pay + pay_b;
-    uint8_t*  d_cmp  = d_out + out_b;
-    uint64_t* d_off  = reinterpret_cast<uint64_t*>(d_cmp + out_b);
-    uint64_t* d_ooff = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(d_off) + off_b);
-    uint32_t* d_len  = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_ooff) + off_b);
-    uint32_t* d_crc  = d_len + MB;
-    uint32_t* d_stat = d_crc + MB;
-    uint32_t* d_hcrc = d_stat + MB;
+    uint8_t*  d_str[2] = {io, io + str_b};
+    uint8_t*  d_hdr    = io + 2 * str_b;
+    uint8_t*  d_pay    = d_hdr + hdr_b;
+    uint8_t*  d_out[2] = {d_pay + pay_b, d_pay + pay_b + out_b};
+    uint8_t*  d_cmp    = d_out[1] + out_b;
+    uint64_t* d_off[2] = {reinterpret_cast<uint64_t*>(d_cmp + out_b), reinterpret_cast<uint64_t*>(d_cmp + out_b + off_b)};
+    uint64_t* d_ooff   = reinterpret_cast<uint64_t*>(d_cmp + out_b + 2 * off_b);
+    uint32_t* d_len    = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(d_ooff) + off_b);
+    uint32_t* d_crc    = d_len + HB;
+    uint32_t* d_stat   = d_crc + HB;
+    uint32_t* d_hcrc   = d_stat + HB;
 
-    const bra_gf_pow_t*   pw = crc_host_pow();
-    std::vector<uint64_t> h_off(MB + 1), h_ooff(MB + 1);
-    std::vector<uint32_t> h_misc(4 * (size_t) MB);
-    uint32_t              crc = crc_chain ? *crc_chain : 0;
-    uint64_t              pos = 0, produced = 0;
-    while (pos < in_size)
+    // walk the stream once on the host: chunk boundaries of every stage (reference chunks.c:338-357, :414)
+    struct Stage
     {
-        // find the chunk boundaries of the next batch (reference chunks.c:338-357, :414)
-        uint32_t nb = 0, max_r = 0, max_c = 0;
-        uint64_t p  = pos;
-        while (nb < MB && p < in_size)
+        uint64_t pos, end;
+        uint32_t nb, max_r, max_c;
+    };
+    std::vector<Stage>    stages;
+    std::vector<uint64_t> offs;  // per stage: nb+1 offsets relative to the stage start, concatenated
+    {
+        uint64_t p = 0;
+        while (p < in_size)
         {
-            if (in_size - p < 267)
+            Stage sg{p, p, 0, 0, 0};
+            while (sg.nb < HB && p < in_size)
             {
-                bra_b200_log_error("bra_b200_decode_host: truncated chunk header at offset %llu", (unsigned long long) p);
-                return 7;
+                if (in_size - p < 267)
+                {
+                    bra_b200_log_error("bra_b200_decode_host: truncated chunk header at offset %llu", (unsigned long long) p);
+                    return 7;
+                }
+                const uint8_t* h = in + p + 3 + 256;
+                const uint32_t r = (uint32_t) h[0] | ((uint32_t) h[1] << 8) | ((uint32_t) h[2] << 16) | ((uint32_t) h[3] << 24);
+                const uint32_t cc = (uint32_t) h[4] | ((uint32_t) h[5] << 8) | ((uint32_t) h[6] << 16) | ((uint32_t) h[7] << 24);
+                if (cc == 0 || r == 0 || cc > PS - 32 || in_size - p - 267 < cc)
+                {
+                    bra_b200_log_error("bra_b200_decode_host: chunk header not valid at offset %llu", (unsigned long long) p);
+                    return 7;
+                }
+                offs.push_back(p - sg.pos);
+                sg.max_r = std::max(sg.max_r, r);
+                sg.max_c = std::max(sg.max_c, cc);
+                p += 267 + cc;
+                ++sg.nb;
             }
-            const uint8_t* h = in + p + 3 + 256;
-            const uint32_t r = (uint32_t) h[0] | ((uint32_t) h[1] << 8) | ((uint32_t) h[2] << 16) | ((uint32_t) h[3] << 24);
-            const uint32_t cc = (uint32_t) h[4] | ((uint32_t) h[5] << 8) | ((uint32_t) h[6] << 16) | ((uint32_t) h[7] << 24);
-            if (cc == 0 || r == 0 || cc > PS - 32 || in_size - p - 267 < cc)
-            {
-                bra_b200_log_error("bra_b200_decode_host: chunk header not valid at offset %llu", (unsigned long long) p);
-                return 7;
-            }
-            h_off[nb] = p - pos;
-            max_r     = std::max(max_r, r);
-            max_c     = std::max(max_c, cc);
-            p += 267 + cc;
-            ++nb;
+            offs.push_back(p - sg.pos);
+            sg.end = p;
+            stages.push_back(sg);
         }
-        h_off[nb] = p - pos;
-        if (cudaMemcpyAsync(d_str, in + pos, p - pos, cudaMemcpyHostToDevice, st) != cudaSuccess) return 4;
-        if (cudaMemcpyAsync(d_off, h_off.data(), ((size_t) nb + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) return 4;
-        const uint32_t gx = bra_div_up(267 + (uint64_t) max_c, 4096);
-        BRA_LAUNCH(P_GLUE, st, stream_scatter_kernel<<<dim3(gx, nb), 256, 0, st>>>(d_str, d_off, d_hdr, d_pay, PS));
-        if (!decode_batch(c, d_hdr, d_pay, nb, max_r, max_c, d_out, d_len, d_crc, d_stat, st)) return 5;
-        if (!crc_headers(d_hdr, 268, nb, d_hcrc, st)) return 5;
-        if (cudaMemcpyAsync(h_misc.data(), d_len, (size_t) 4 * MB * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+    }
+    const bra_gf_pow_t*   pw = crc_host_pow();
+    std::vector<uint64_t> h_ooff(HB + 1);
+    std::vector<uint32_t> h_misc(4 * (size_t) HB);
+    uint32_t              crc = crc_chain ? *crc_chain : 0;
+    uint64_t              produced = 0;
+    std::vector<size_t>   off_base(stages.size() + 1, 0);
+    for (size_t i = 0; i < stages.size(); ++i) off_base[i + 1] = off_base[i] + stages[i].nb + 1;
+
+    auto upload = [&](size_t i, int slot) -> bool {
+        const Stage& sg = stages[i];
+        if (cudaMemcpyAsync(d_str[slot], in + sg.pos, sg.end - sg.pos, cudaMemcpyHostToDevice, P.s_in) != cudaSuccess) return false;
+        if (cudaMemcpyAsync(d_off[slot], offs.data() + off_base[i], ((size_t) sg.nb + 1) * 8, cudaMemcpyHostToDevice, P.s_in) != cudaSuccess) return false;
+        cudaEventRecord(P.ev_in[slot], P.s_in);
+        return true;
+    };
+    if (!stages.empty() && !upload(0, 0)) return 4;
+    for (size_t i = 0; i < stages.size(); ++i)
+    {
+        const int    slot = (int) (i & 1);
+        const Stage& sg   = stages[i];
+        if (i + 1 < stages.size())
+        {
+            if (i >= 1) cudaStreamWaitEvent(P.s_in, P.ev_comp[slot ^ 1], 0);
+            if (!upload(i + 1, slot ^ 1)) return 4;
+        }
+        cudaStreamWaitEvent(st, P.ev_in[slot], 0);
+        if (i >= 2) cudaStreamWaitEvent(st, P.ev_out[slot], 0);  // output slot free once stage i-2 has been copied out
+        const uint32_t gx = bra_div_up(267 + (uint64_t) sg.max_c, 4096);
+        BRA_LAUNCH(P_GLUE, st, stream_scatter_kernel<<<dim3(gx, sg.nb), 256, 0, st>>>(d_str[slot], d_off[slot], d_hdr, d_pay, PS));
+        if (!decode_batch(c, d_hdr, d_pay, sg.nb, sg.max_r, sg.max_c, d_out[slot], d_len, d_crc, d_stat, st)) return 5;
+        if (!crc_headers(d_hdr, 268, sg.nb, d_hcrc, st)) return 5;
+        if (cudaMemcpyAsync(h_misc.data(), d_len, (size_t) 4 * HB * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
         if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
         uint64_t o = 0;
-        for (uint32_t b = 0; b < nb; ++b)
+        bool     contiguous = true;
+        for (uint32_t b = 0; b < sg.nb; ++b)
         {
-            if (h_misc[2 * (size_t) MB + b] != 0)
+            if (h_misc[2 * (size_t) HB + b] != 0)
             {
-                bra_b200_log_error("bra_b200_decode_host: chunk %u of the batch at offset %llu is corrupt", b, (unsigned long long) pos);
+                bra_b200_log_error("bra_b200_decode_host: chunk %u of the batch at offset %llu is corrupt", b, (unsigned long long) sg.pos);
                 return 8;
             }
             h_ooff[b] = o;
             o += h_misc[b];
-            crc = bra_crc_combine(pw, crc, h_misc[3 * (size_t) MB + b], 268);  // chunks.c:396
-            crc = bra_crc_combine(pw, crc, h_misc[(size_t) MB + b], h_misc[b]); // chunks.c:397
+            if (b + 1 < sg.nb) contiguous &= h_misc[b] == S;
+            crc = bra_crc_combine(pw, crc, h_misc[3 * (size_t) HB + b], 268);   // chunks.c:396
+            crc = bra_crc_combine(pw, crc, h_misc[(size_t) HB + b], h_misc[b]); // chunks.c:397
         }
-        h_ooff[nb] = o;
+        h_ooff[sg.nb] = o;
         if (produced + o > out_cap)
         {
             bra_b200_log_error("bra_b200_decode_host: output buffer too small");
             return 6;
         }
         // full blocks are already contiguous; compact only when some block is short
-        const uint8_t* src = d_out;
-        bool           contiguous = true;
-        for (uint32_t b = 0; b + 1 < nb; ++b) contiguous &= h_misc[b] == S;
+        const uint8_t* src = d_out[slot];
         if (!contiguous)
         {
-            if (cudaMemcpyAsync(d_ooff, h_ooff.data(), ((size_t) nb + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) return 4;
-            BRA_LAUNCH(P_GLUE, st, compact_out_kernel<<<dim3(bra_div_up(S, 4096), nb), 256, 0, st>>>(d_out, S, d_len, d_ooff, d_cmp));
-            src = d_cmp;
+            if (cudaMemcpyAsync(d_ooff, h_ooff.data(), ((size_t) sg.nb + 1) * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) return 4;
+            BRA_LAUNCH(P_GLUE, st, compact_out_kernel<<<dim3(bra_div_up(S, 4096), sg.nb), 256, 0, st>>>(d_out[slot], S, d_len, d_ooff, d_cmp));
+            if (cudaStreamSynchronize(st) != cudaSuccess) return 4;  // d_cmp is single-buffered: drain it before the next stage
+            if (cudaMemcpyAsync(out + produced, d_cmp, o, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+            if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
+            cudaEventRecord(P.ev_comp[slot], st);
+            cudaEventRecord(P.ev_out[slot], st);
         }
-        if (cudaMemcpyAsync(out + produced, src, o, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
-        if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
+        else
+        {
+            cudaEventRecord(P.ev_comp[slot], st);
+            cudaStreamWaitEvent(P.s_out, P.ev_comp[slot], 0);
+            if (cudaMemcpyAsync(out + produced, src, o, cudaMemcpyDeviceToHost, P.s_out) != cudaSuccess) return 4;
+            cudaEventRecord(P.ev_out[slot], P.s_out);
+        }
         produced += o;
-        pos = p;
     }
+    if (cudaStreamSynchronize(P.s_out) != cudaSuccess || cudaStreamSynchronize(P.s_in) != cudaSuccess) return 4;
     *out_size = produced;
     if (crc_chain) *crc_chain = crc;
     return 0;
