@@ -285,9 +285,16 @@ def main():
                      "huf_dec_sync": c_sum * share, "huf_dec_write": (c_sum + r_sum) * share, "huf_pack": (r_sum + c_sum) * share,
                      "rle_enc_emit": elems + r_sum * share, "rle_dec_expand": elems + r_sum * share}
         alg_bytes = alg_table.get(fam)
+        traffic = None
+        try:
+            per_elem = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(fam)
+            if isinstance(per_elem, (int, float)):
+                traffic = per_elem * elems  # measured DRAM bytes per element (ncu --set full, see the file) x elements per launch
+        except OSError:
+            pass
         roof = {"bound": "hbm", "kernel": fam, "launches": fam_launches, "avg_launch_ms": fam_ms / max(fam_launches, 1),
                 "share_of_kernel_time": fam_ms / kernel_ms if kernel_ms else None, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
-                "traffic": None}
+                "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (ncu dram__bytes per element x elements per launch)" if traffic else None}
         if alg_bytes:
             roof["alg_bytes_per_launch"] = alg_bytes
             roof["achieved"] = alg_bytes / (roof["avg_launch_ms"] / 1e3) / 1e9

@@ -386,15 +386,39 @@ __global__ void bwt_reset_stats_kernel(const uint8_t* __restrict__ skip, uint32_
 // directly (bytes h .. h+FIN_DEPTH-1; everything before is known equal). Every member counts the
 // members that sort before it, so the kernel is fully parallel. Members still equal after FIN_DEPTH
 // bytes stay one group (in their current order) and go on with prefix doubling.
+// Compares rotations a and c over bytes [from, from+FIN_DEPTH) (from already reduced mod p); four bytes per
+// step through aligned word loads while neither side is about to wrap, bytes otherwise.
+__device__ __forceinline__ uint32_t load_be32(const uint8_t* __restrict__ T, uint32_t i)
+{
+    const uint32_t* Tw = reinterpret_cast<const uint32_t*>(T);
+    const uint32_t  w0 = Tw[i >> 2], w1 = Tw[(i >> 2) + 1];
+    return __byte_perm(__funnelshift_r(w0, w1, (i & 3u) * 8), 0, 0x0123);  // bytes i..i+3, first byte most significant
+}
+
 __device__ __forceinline__ int rot_cmp_window(const uint8_t* __restrict__ T, uint32_t p, uint32_t a, uint32_t c, uint32_t from)
 {
-    uint32_t ia = (a + from) % p, ic = (c + from) % p;
-    for (uint32_t k = 0; k < FIN_DEPTH; ++k)
+    uint32_t ia = a + from, ic = c + from;
+    if (ia >= p) ia -= p;
+    if (ic >= p) ic -= p;
+    uint32_t k = 0;
+    while (k < FIN_DEPTH)
     {
-        const uint8_t x = T[ia], y = T[ic];
-        if (x != y) return x < y ? -1 : 1;
-        if (++ia == p) ia = 0;
-        if (++ic == p) ic = 0;
+        if (ia + 8 <= p && ic + 8 <= p)  // both windows (plus the second word of the unaligned read) stay inside the block
+        {
+            const uint32_t x = load_be32(T, ia), y = load_be32(T, ic);
+            if (x != y) return x < y ? -1 : 1;
+            ia += 4;
+            ic += 4;
+            k += 4;
+        }
+        else
+        {
+            const uint8_t x = T[ia], y = T[ic];
+            if (x != y) return x < y ? -1 : 1;
+            if (++ia == p) ia = 0;
+            if (++ic == p) ic = 0;
+            ++k;
+        }
     }
     return 0;
 }
@@ -413,6 +437,7 @@ __global__ void __launch_bounds__(EW_THREADS)
     const uint8_t* T    = in + base;
     const uint8_t* fo   = flags_old + base;
     const uint32_t tend = min(p, tile0 + EW_TILE);
+    const uint32_t hm   = h % p;
     uint32_t       heads = 0;
     int            best  = -1;  // last head that lands in this tile
     __shared__ int      s_best[8];
@@ -431,7 +456,7 @@ __global__ void __launch_bounds__(EW_THREADS)
             for (uint32_t m = s; m < e; ++m)
             {
                 if (m == j) continue;
-                const int c = rot_cmp_window(T, p, me, sa[base + m], h);
+                const int c = rot_cmp_window(T, p, me, sa[base + m], hm);
                 if (c > 0)
                     ++less;
                 else if (c == 0 && m < j)
@@ -824,9 +849,8 @@ uint32_t ibwt_row_stride(uint32_t max_n)
 }
 uint32_t ibwt_kmax(uint32_t max_n) { return (max_n + ibwt_row_stride(max_n) - 1) / ibwt_row_stride(max_n) + 1; }
 
-bool bwt_inverse_batch(const BwtInvArgs& a, cudaStream_t st)
+static bool bwt_inverse_chunk(const BwtInvArgs& a, cudaStream_t st)
 {
-    if (a.nblk == 0 || a.max_n == 0) return true;
     const uint32_t R = ibwt_row_stride(a.max_n), kmax = ibwt_kmax(a.max_n);
     if (!radix_pass_u8_index_packed(a.d_in, a.d_W, a.stride, a.d_len, a.max_n, a.nblk, a.d_hist, st)) return false;
     const dim3 grid(bra_div_up(kmax, IB_THREADS), a.nblk);
@@ -837,6 +861,14 @@ bool bwt_inverse_batch(const BwtInvArgs& a, cudaStream_t st)
     BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_walk_emit_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_out));
     BRA_CUDA_TRY(cudaGetLastError());
     return true;
+}
+
+// One call over the whole batch. (Building and walking W in L2-sized chunks of blocks was measured and is
+// slower: with ~24 blocks per chunk the walk kernels are bound by the longest single walk, not by bandwidth.)
+bool bwt_inverse_batch(const BwtInvArgs& a, cudaStream_t st)
+{
+    if (a.nblk == 0 || a.max_n == 0) return true;
+    return bwt_inverse_chunk(a, st);
 }
 
 }  // namespace bra
