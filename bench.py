@@ -40,12 +40,14 @@ def make_workload(pkg, kind, nbytes, seed):
         return pkg.gen_random(nbytes, seed + 1)
     if kind == "periodic":
         return pkg.gen_periodic(nbytes, b"0123456789abcdef")
+    if kind == "repeat251":
+        return pkg.gen_periodic(nbytes, pkg.gen_random(251, 4).tobytes())  # C4b: long repeats, period does not divide the block
     raise SystemExit(f"unknown workload {kind}")
 
 
 def workload_name(kind, nbytes, block):
     names = {"text": "synthetic English-like text (lorem vocabulary, splitmix64)", "random": "uniform random bytes (splitmix64)",
-             "periodic": "period-16 text"}
+             "periodic": "period-16 text", "repeat251": "251-byte random pattern repeated (long repeats, not cyclic)"}
     return f"{nbytes / 2**30:g} GiB {names[kind]}, {block // 1024} KiB blocks"
 
 
@@ -138,7 +140,7 @@ def main():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="text", choices=["text", "random", "periodic"])
+    ap.add_argument("--workload", default="text", choices=["text", "random", "periodic", "repeat251"])
     ap.add_argument("--size-mib", type=int, default=1024)
     ap.add_argument("--block-kib", type=int, default=1024)
     ap.add_argument("--batch", type=int, default=1024, help="blocks per internal batch (bounds device workspace)")

@@ -1,9 +1,10 @@
-// sort.cu -- batched, segmented, stable LSD radix-sort pass (8- or 10-bit digit).
+// sort.cu -- batched, segmented, stable LSD radix-sort pass (8-bit digit; the kernels are templated on the digit width).
 //
 // Used three ways on the hot path:
-//   * forward BWT: initial sort of rotation indices by their first 4 bytes (4 passes of 8 bits) and
-//     the per-doubling-round stable re-bucketing by rank (2 passes of 10 bits for blocks up to 1 MiB,
-//     3 passes of 8 bits above)  -- replaces the qsort_r call of reference src/encoders/bra_bwt.c:91;
+//   * forward BWT: initial sort of rotation indices by their first 4 bytes (4 passes) and the
+//     per-doubling-round stable re-bucketing by rank (2-3 passes) -- replaces the qsort_r call of
+//     reference src/encoders/bra_bwt.c:91. (A 10-bit digit, 2 passes per round, was measured: the wider
+//     shared-memory counters and 4-element output runs make each pass ~1.7x slower, a net loss.)
 //   * inverse BWT: one 8-bit pass with the BWT bytes as keys builds `transform[]`, i.e. the stable
 //     counting sort of reference bra_bwt.c:142-159.
 //
@@ -248,15 +249,13 @@ static bool radix_pass_t(const KeyT* keys, const uint32_t* vals, KeyT* keys_out,
     return true;
 }
 
-// sized for the widest digit in use
-size_t radix_hist_bytes(uint32_t max_len, uint32_t nblk) { return (size_t) nblk * 1024 * bra_div_up(max_len, RS_TILE) * sizeof(uint32_t); }
+size_t radix_hist_bytes(uint32_t max_len, uint32_t nblk) { return (size_t) nblk * 256 * bra_div_up(max_len, RS_TILE) * sizeof(uint32_t); }
 
 bool radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t stride,
                     const uint32_t* d_len, const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t bits,
                     bool hist_ready, uint32_t* d_hist, cudaStream_t st)
 {
-    if (bits == 10)
-        return radix_pass_t<10, uint32_t, false, 0>(keys, vals, keys_out, vals_out, stride, d_len, d_skip, max_len, nblk, shift, hist_ready, d_hist, st);
+    (void) bits;  // only the 8-bit digit is instantiated
     return radix_pass_t<8, uint32_t, false, 0>(keys, vals, keys_out, vals_out, stride, d_len, d_skip, max_len, nblk, shift, hist_ready, d_hist, st);
 }
 
