@@ -363,3 +363,64 @@ def test_reference_unit_test_programs_pass_against_the_dropin(golden, tmp_path):
         ran += 1
     if ran == 0:
         pytest.skip("oracle/_ref test programs not built (needs /root/reference at build time)")
+
+
+def test_batched_fuzz_shapes(pkg, oracle, vocab):
+    """Many small batches with odd block sizes, ragged tails and mixed content, every block compared with the oracle."""
+    rng = random.Random(12)
+    nrng = np.random.default_rng(12)
+    for it in range(10):
+        block = rng.choice([16, 48, 256, 4096, 4112, 8192 + 16, 12288, 20000 - 20000 % 16])
+        nblk = rng.choice([1, 2, 3, 5, 9])
+        tail = rng.randrange(1, block + 1)
+        n = (nblk - 1) * block + tail
+        kind = it % 5
+        if kind == 0:
+            data = _text(pkg, vocab, n, seed=it)
+        elif kind == 1:
+            data = nrng.integers(0, 256, n, dtype=np.uint8).tobytes()
+        elif kind == 2:
+            data = _runs(rng, n)
+        elif kind == 3:
+            p = bytes(rng.randrange(4) for _ in range(rng.choice([1, 2, 3, 8, 16, 48])))
+            data = (p * (n // len(p) + 1))[:n]
+        else:
+            data = nrng.integers(0, 3, n, dtype=np.uint8).tobytes()
+        _check_batch(pkg, oracle, data, block, max_batch=rng.choice([1, 2, 4, 16]))
+
+
+# ------------------------------------------------------------------------------------------ the reference CLI as a drop-in
+def test_reference_cli_packs_identical_archives_with_the_dropin(pkg, golden, tmp_path):
+    """oracle/_ref/bra_gpu / unbra_gpu are the reference's own bra and unbra programs linked against
+    libbra_b200.so in place of its five hot-path sources (oracle/Makefile: ref_cli). `bra -c` must write
+    byte-identical .BRa archives to the ones the unmodified reference wrote
+    (tests/golden/reference_archives.json), and `unbra` must test and extract them."""
+    import hashlib
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bra, unbra = os.path.join(root, "oracle", "_ref", "bra_gpu"), os.path.join(root, "oracle", "_ref", "unbra_gpu")
+    if not (os.path.exists(bra) and os.path.exists(unbra)):
+        pytest.skip("oracle/_ref CLI binaries not built (needs /root/reference at build time)")
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from make_golden_archives import inputs
+    arcs = json.load(open(os.path.join(root, "tests", "golden", "reference_archives.json")))["archives"]
+    for name, data in inputs(pkg, golden).items():
+        exp = arcs[name]
+        assert hashlib.sha256(data).hexdigest() == exp["input_sha256"], name
+        (tmp_path / name).write_bytes(data)
+        r = subprocess.run([bra, "-c", "-o", name + ".BRa", name], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (name, r.stdout[-1500:], r.stderr[-1500:])
+        got = (tmp_path / (name + ".BRa")).read_bytes()
+        assert len(got) == exp["size"], (name, len(got), exp["size"])
+        assert int.from_bytes(got[-4:], "little") == exp["entry_crc32c"], name
+        assert hashlib.sha256(got).hexdigest() == exp["sha256"], name
+        if "hex" in exp:
+            assert got == H(exp["hex"]), _first_diff(got, H(exp["hex"]))
+        r = subprocess.run([unbra, "-t", name + ".BRa"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (name, r.stdout[-1500:], r.stderr[-1500:])
+        r = subprocess.run([unbra, "-y", "-o", "out", name + ".BRa"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (name, r.stdout[-1500:], r.stderr[-1500:])
+        assert (tmp_path / "out" / name).read_bytes() == data, name
