@@ -390,18 +390,20 @@ def test_batched_fuzz_shapes(pkg, oracle, vocab):
 
 
 # ------------------------------------------------------------------------------------------ the reference CLI as a drop-in
-def test_reference_cli_packs_identical_archives_with_the_dropin(pkg, golden, tmp_path):
+@pytest.mark.parametrize("suffix", ["gpu", "gpu2"])
+def test_reference_cli_packs_identical_archives_with_the_dropin(pkg, golden, tmp_path, suffix):
     """oracle/_ref/bra_gpu / unbra_gpu are the reference's own bra and unbra programs linked against
-    libbra_b200.so in place of its five hot-path sources (oracle/Makefile: ref_cli). `bra -c` must write
-    byte-identical .BRa archives to the ones the unmodified reference wrote
-    (tests/golden/reference_archives.json), and `unbra` must test and extract them."""
+    libbra_b200.so in place of its five hot-path sources; bra_gpu2 / unbra_gpu2 additionally replace the
+    reference's chunk loop by the batched seam br-archive_b200/seam/lib_bra_io_file_chunks_b200.c
+    (oracle/Makefile: ref_cli). `bra -c` must write byte-identical .BRa archives to the ones the unmodified
+    reference wrote (tests/golden/reference_archives.json), and `unbra` must list, test and extract them."""
     import hashlib
     import json
     import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    bra, unbra = os.path.join(root, "oracle", "_ref", "bra_gpu"), os.path.join(root, "oracle", "_ref", "unbra_gpu")
+    bra, unbra = os.path.join(root, "oracle", "_ref", "bra_" + suffix), os.path.join(root, "oracle", "_ref", "unbra_" + suffix)
     if not (os.path.exists(bra) and os.path.exists(unbra)):
         pytest.skip("oracle/_ref CLI binaries not built (needs /root/reference at build time)")
     sys.path.insert(0, os.path.join(root, "tests", "golden"))
@@ -419,8 +421,9 @@ def test_reference_cli_packs_identical_archives_with_the_dropin(pkg, golden, tmp
         assert hashlib.sha256(got).hexdigest() == exp["sha256"], name
         if "hex" in exp:
             assert got == H(exp["hex"]), _first_diff(got, H(exp["hex"]))
-        r = subprocess.run([unbra, "-t", name + ".BRa"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
-        assert r.returncode == 0, (name, r.stdout[-1500:], r.stderr[-1500:])
+        for flag in ("-l", "-t"):
+            r = subprocess.run([unbra, flag, name + ".BRa"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, (name, flag, r.stdout[-1500:], r.stderr[-1500:])
         r = subprocess.run([unbra, "-y", "-o", "out", name + ".BRa"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, (name, r.stdout[-1500:], r.stderr[-1500:])
         assert (tmp_path / "out" / name).read_bytes() == data, name

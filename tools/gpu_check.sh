@@ -8,7 +8,7 @@ nproc > gpurun_out/nproc.txt
 tests=$(python -m pytest tests/test_gpu_parity.py -m gpu --collect-only -q 2>/dev/null | grep "::")
 : > gpurun_out/summary.txt
 for t in $tests; do
-    name=$(echo "$t" | sed 's/.*:://')
+    name=$(echo "$t" | sed 's/.*:://' | tr '[]' '__')
     timeout ${PER_TEST_TIMEOUT:-420} python -m pytest "$t" -x -q -m gpu > "gpurun_out/tests/$name.log" 2>&1
     rc=$?
     echo "$rc $name" >> gpurun_out/summary.txt
