@@ -260,12 +260,14 @@ __global__ void __launch_bounds__(EW_THREADS)
 __global__ void __launch_bounds__(EW_THREADS)
     bwt_ranks_kernel(const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ flags_old, uint64_t stride,
                      const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, const int* __restrict__ tile_last, uint32_t tiles,
-                     uint32_t* __restrict__ rank_out, uint32_t* __restrict__ maxgroup, unsigned long long* __restrict__ sumsq)
+                     uint32_t* __restrict__ rank_out, uint32_t* __restrict__ maxgroup, unsigned long long* __restrict__ sumsq,
+                     const uint32_t* __restrict__ ngroups)
 {
     __shared__ int red[33];
     const uint32_t b = blockIdx.y;
     if (skip[b]) return;
     const uint32_t p     = period[b];
+    if (ngroups[b] >= p) return;  // every group is a singleton: the block is finished, nobody will read its ranks
     const uint32_t tile0 = blockIdx.x * EW_TILE;
     if (tile0 >= p) return;
     const uint64_t base = (uint64_t) b * stride;
@@ -668,7 +670,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<0><<<grid, EW_THREADS, 0, st>>>(kA, vA, nullptr, 0, a.stride, a.d_period, a.d_done, nullptr, fcur, a.d_tile_last, tiles,
                                                       a.d_ngroups));
     BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fcur, nullptr, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
-                                                                          a.d_maxgroup, a.d_sumsq));
+                                                                          a.d_maxgroup, a.d_sumsq, a.d_ngroups));
 
     uint32_t h = 4, rounds = 0, finishes = 0;
     uint32_t key_bits = 1;
@@ -691,7 +693,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             BRA_LAUNCH(P_BWT_FINISH, st, bwt_finish_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, a.d_finskip, h, vA, fcur, vB, fnext,
                                                                                      a.d_tile_last, tiles, a.d_ngroups));
             BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vB, fnext, fcur, a.stride, a.d_period, a.d_finskip, a.d_tile_last, tiles, rk,
-                                                                                  a.d_maxgroup, a.d_sumsq));
+                                                                                  a.d_maxgroup, a.d_sumsq, a.d_ngroups));
             BRA_LAUNCH(P_BWT_FINISH, st, bwt_copyback_kernel<<<grid, EW_THREADS, 0, st>>>(a.stride, a.d_period, a.d_finskip, vB, vA, fnext, fcur));
             ++finishes;
             continue;
@@ -714,7 +716,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(nullptr, vA, rk, h, a.stride, a.d_period, a.d_done, fcur, fnext, a.d_tile_last, tiles,
                                                           a.d_ngroups));
         BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
-                                                                              a.d_maxgroup, a.d_sumsq));
+                                                                              a.d_maxgroup, a.d_sumsq, a.d_ngroups));
         std::swap(fcur, fnext);
         h *= 2;
         ++rounds;

@@ -148,20 +148,30 @@ __global__ void __launch_bounds__(RS_THREADS, 4)
         const uint32_t e = w * 512 + r * 32 + l;
         k[r]             = e < tn ? keys[base + tile0 + e] : (KeyT) 0;
     }
+    // Phase A: the peer masks of all 16 rounds are independent of each other -- issue every match first so
+    // that their latency overlaps (the profile showed the warp waiting on one match at a time otherwise).
+    uint32_t peers[RS_ITEMS];
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+    {
+        const uint32_t e = w * 512 + r * 32 + l;
+        const uint32_t d = e < tn ? rs_digit<BITS>(k[r], shift) : RADIX;  // RADIX = padding, matches only padding
+        peers[r]         = __match_any_sync(BRA_FULL, d);
+    }
+    // Phase B: running per-warp digit counters, one round after the other (memory order = stability)
 #pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r)
     {
         const uint32_t e  = w * 512 + r * 32 + l;
         const bool     ok = e < tn;
-        const uint32_t d  = ok ? rs_digit<BITS>(k[r], shift) : RADIX;  // RADIX = padding, matches only padding
-        const uint32_t peers = __match_any_sync(BRA_FULL, d);
-        const uint32_t before = __popc(peers & lanemask_lt());
-        const int      leader = __ffs(peers) - 1;
+        const uint32_t d  = ok ? rs_digit<BITS>(k[r], shift) : RADIX;
+        const uint32_t before = __popc(peers[r] & lanemask_lt());
+        const int      leader = __ffs(peers[r]) - 1;
         uint32_t       old    = 0;
         if (ok && (int) l == leader)
         {
             old          = S.wcnt[w][d];
-            S.wcnt[w][d] = (unsigned short) (old + __popc(peers));
+            S.wcnt[w][d] = (unsigned short) (old + __popc(peers[r]));
         }
         old   = __shfl_sync(BRA_FULL, old, leader);
         rk[r] = (unsigned short) (old + before);
