@@ -72,8 +72,12 @@ __device__ __forceinline__ uint32_t lane_mtf_encode(uint64_t* Q, uint32_t x)
     }
 }
 
-// One segment per lane. MODE 0: encode (symbols -> ranks), 1: decode (ranks -> symbols),
-// 2: decode summary (no output; the final list is the position permutation of the segment).
+// One segment per lane. MODE 0: encode (symbols -> ranks) from the segment's entry list.
+// MODE 2: decode from the IDENTITY list: the output is, per rank, the entry-list POSITION of the decoded
+// symbol ("relative symbol"), and the final list is the position permutation of the segment (its summary).
+// After the per-block scan has produced the entry lists, mtf_map_kernel turns relative symbols into symbols
+// with a 256-entry table lookup -- so decoding replays each segment once, not twice.
+// (MODE 1, decode from a known entry list, is kept for completeness; the batch path does not use it.)
 template <int MODE>
 __global__ void __launch_bounds__(MTF_LANE_WARPS * 32)
     mtf_lane_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t stride, const uint32_t* __restrict__ len, uint32_t segs,
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(MTF_LANE_WARPS * 32)
     }
 
     const uint8_t* ip = in + off;
-    uint8_t*       op = (MODE == 2) ? nullptr : out + off;
+    uint8_t*       op = out + off;
     uint32_t       i  = 0;
     for (; i + 16 <= m; i += 16)
     {
@@ -126,13 +130,13 @@ __global__ void __launch_bounds__(MTF_LANE_WARPS * 32)
             }
             ow[q] = o;
         }
-        if (MODE != 2) *reinterpret_cast<uint4*>(op + i) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(op + i) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
     for (; i < m; ++i)
     {
         const uint32_t x = ip[i];
         const uint32_t r = (MODE == 0) ? lane_mtf_encode(W, x) : lane_mtf_decode(W, x);
-        if (MODE != 2) op[i] = (uint8_t) r;
+        op[i] = (uint8_t) r;
     }
     if (MODE == 2)
     {
@@ -251,6 +255,33 @@ __global__ void __launch_bounds__(32)
     }
 }
 
+// relative symbols -> symbols: out[i] = entry_list_of_segment[out[i]], in place
+__global__ void __launch_bounds__(256)
+    mtf_map_kernel(uint8_t* __restrict__ data, uint64_t stride, const uint32_t* __restrict__ len, uint32_t segs, const uint8_t* __restrict__ state)
+{
+    __shared__ uint8_t lut[256];
+    const uint32_t b = blockIdx.y, seg = blockIdx.x;
+    const uint32_t n = len[b];
+    if ((uint64_t) seg * MTF_SEG >= n) return;
+    const uint32_t m = min((uint32_t) MTF_SEG, n - seg * MTF_SEG);
+    lut[threadIdx.x] = state[((uint64_t) b * segs + seg) * 256 + threadIdx.x];
+    __syncthreads();
+    uint8_t*       p = data + (uint64_t) b * stride + (uint64_t) seg * MTF_SEG;
+    const uint32_t i = threadIdx.x * 16;
+    if (i + 16 <= m)
+    {
+        uint4    v    = *reinterpret_cast<uint4*>(p + i);
+        uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            w[q] = (uint32_t) lut[w[q] & 0xFFu] | ((uint32_t) lut[(w[q] >> 8) & 0xFFu] << 8) | ((uint32_t) lut[(w[q] >> 16) & 0xFFu] << 16) |
+                   ((uint32_t) lut[w[q] >> 24] << 24);
+        *reinterpret_cast<uint4*>(p + i) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    else
+        for (uint32_t k = i; k < m; ++k) p[k] = lut[p[k]];
+}
+
 uint32_t mtf_segments(uint32_t max_n) { return bra_div_up(max_n, MTF_SEG); }
 
 bool mtf_encode_batch(const uint8_t* d_in, uint8_t* d_out, uint64_t stride, const uint32_t* d_len, uint32_t max_n, uint32_t nblk,
@@ -273,9 +304,9 @@ bool mtf_decode_batch(const uint8_t* d_in, uint8_t* d_out, uint64_t stride, cons
     if (nblk == 0 || max_n == 0) return true;
     const uint32_t segs = mtf_segments(max_n);
     const dim3     lgrid(bra_div_up(segs, MTF_LANE_WARPS * 32), nblk);
-    BRA_LAUNCH(P_MTF_SUMMARY, st, mtf_lane_kernel<2><<<lgrid, MTF_LANE_WARPS * 32, 0, st>>>(d_in, nullptr, stride, d_len, segs, nullptr, d_summ));
+    BRA_LAUNCH(P_MTF_APPLY, st, mtf_lane_kernel<2><<<lgrid, MTF_LANE_WARPS * 32, 0, st>>>(d_in, d_out, stride, d_len, segs, nullptr, d_summ));
     BRA_LAUNCH(P_MTF_SCAN, st, mtf_scan_kernel<false><<<nblk, 32, 0, st>>>(d_summ, nullptr, d_len, segs, d_state));
-    BRA_LAUNCH(P_MTF_APPLY, st, mtf_lane_kernel<1><<<lgrid, MTF_LANE_WARPS * 32, 0, st>>>(d_in, d_out, stride, d_len, segs, d_state, nullptr));
+    BRA_LAUNCH(P_MTF_SUMMARY, st, mtf_map_kernel<<<dim3(segs, nblk), 256, 0, st>>>(d_out, stride, d_len, segs, d_state));
     BRA_CUDA_TRY(cudaGetLastError());
     return true;
 }
