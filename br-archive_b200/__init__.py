@@ -208,7 +208,7 @@ class Context:
     def stats(self):
         r, s, l = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0)
         self.L.bra_b200_last_stats(self.handle, C.byref(r), C.byref(s), C.byref(l))
-        return {"bwt_rounds": r.value, "huf_sweeps": s.value}
+        return {"bwt_rounds": r.value, "huf_sweeps": s.value, "launches": l.value}
 
     # ---- device-resident -------------------------------------------------------------------
     def alloc_encode_outputs(self, nblk: int):

@@ -19,6 +19,7 @@ enum ProfId
 };
 void prof_pre(int id, cudaStream_t st);
 void prof_post(int id, cudaStream_t st);
+uint64_t prof_total_launches();
 // every kernel launch of the library goes through this macro
 #define BRA_LAUNCH(id, st, ...)  \
     do                           \
@@ -43,8 +44,6 @@ bool   radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys
                       uint32_t* d_hist, cudaStream_t st);
 bool   radix_pass_u8_index_packed(const uint8_t* keys, uint32_t* packed_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len,
                                   uint32_t nblk, uint32_t* d_hist, cudaStream_t st);
-bool   radix_pass_u8_index(const uint8_t* keys, uint32_t* vals_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len, uint32_t nblk,
-                           uint32_t* d_hist, cudaStream_t st);
 
 // ---- bwt.cu -------------------------------------------------------------------------------
 struct BwtFwdArgs

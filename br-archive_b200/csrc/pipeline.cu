@@ -394,6 +394,7 @@ extern "C" int bra_b200_encode_device(bra_b200_ctx_t* c, const uint8_t* d_in, ui
     if (!ctx_bind(c)) return 2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     c->last_rounds  = 0;
+    const uint64_t launches0 = prof_total_launches();
     for (uint32_t b0 = 0; b0 < nblk; b0 += c->max_batch)
     {
         const uint32_t nb = std::min(c->max_batch, nblk - b0);
@@ -403,6 +404,7 @@ extern "C" int bra_b200_encode_device(bra_b200_ctx_t* c, const uint8_t* d_in, ui
             return 3;
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
+    c->last_launches = prof_total_launches() - launches0;
     return 0;
 }
 
@@ -418,6 +420,7 @@ extern "C" int bra_b200_decode_device(bra_b200_ctx_t* c, const uint8_t* d_hdr, c
     if (!ctx_bind(c)) return 2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     c->last_sweeps  = 0;
+    const uint64_t launches0 = prof_total_launches();
     for (uint32_t b0 = 0; b0 < nblk; b0 += c->max_batch)
     {
         const uint32_t nb = std::min(c->max_batch, nblk - b0);
@@ -426,6 +429,7 @@ extern "C" int bra_b200_decode_device(bra_b200_ctx_t* c, const uint8_t* d_hdr, c
             return 3;
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
+    c->last_launches = prof_total_launches() - launches0;
     return 0;
 }
 

@@ -59,6 +59,13 @@ void prof_post(int id, cudaStream_t st)
     if (!g_slots[id].pending.empty()) cudaEventRecord(g_slots[id].pending.back().second, st);
 }
 
+uint64_t prof_total_launches()
+{
+    uint64_t t = 0;
+    for (int i = 0; i < P_COUNT; ++i) t += g_slots[i].launches.load(std::memory_order_relaxed);
+    return t;
+}
+
 static void prof_drain()
 {
     for (int i = 0; i < P_COUNT; ++i)

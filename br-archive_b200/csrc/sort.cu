@@ -107,7 +107,7 @@ struct RsSmem
     static constexpr uint32_t RADIX = 1u << BITS;
     unsigned short            wcnt[8][RADIX];  // per-warp digit counters -> per-warp bases (< 4096)
     unsigned short            dstart[RADIX];   // start of each digit's run inside the sorted tile
-    uint32_t                  goff[RADIX];     // global destination of each digit's run for this tile
+    uint32_t                  gdelta[RADIX];   // (global destination of the digit's run for this tile) - dstart, mod 2^32
     KeyT                      skey[RS_TILE];
     uint32_t                  sval[RS_TILE];
     uint32_t                  red[34];
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4)
         {
             const uint32_t d = threadIdx.x * DPT + i;
             S.dstart[d]      = (unsigned short) ex;
-            S.goff[d]        = hist[((uint64_t) b * RADIX + d) * tiles + t];
+            S.gdelta[d]      = hist[((uint64_t) b * RADIX + d) * tiles + t] - ex;
             ex += tot[i];
         }
     }
@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(RS_THREADS, 4)
     {
         const KeyT     kk  = S.skey[e];
         const uint32_t d   = rs_digit<BITS>(kk, shift);
-        const uint64_t dst = base + S.goff[d] + (e - S.dstart[d]);
+        const uint64_t dst = base + (uint32_t) (S.gdelta[d] + e);
         if (OUT_MODE == 0)
         {
             keys_out[dst] = kk;
@@ -273,12 +273,6 @@ bool radix_pass_u8_index_packed(const uint8_t* keys, uint32_t* packed_out, uint6
                                 uint32_t nblk, uint32_t* d_hist, cudaStream_t st)
 {
     return radix_pass_t<8, uint8_t, true, 2>(keys, nullptr, nullptr, packed_out, stride, d_len, nullptr, max_len, nblk, 0, false, d_hist, st);
-}
-
-bool radix_pass_u8_index(const uint8_t* keys, uint32_t* vals_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len, uint32_t nblk,
-                         uint32_t* d_hist, cudaStream_t st)
-{
-    return radix_pass_t<8, uint8_t, true, 1>(keys, nullptr, nullptr, vals_out, stride, d_len, nullptr, max_len, nblk, 0, false, d_hist, st);
 }
 
 }  // namespace bra
