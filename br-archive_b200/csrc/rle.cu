@@ -384,8 +384,10 @@ __device__ __forceinline__ uint32_t rle_tok_out(uint8_t c)  // bytes of output i
     return s >= 0 ? (uint32_t) s + 1u : (s == -128 ? 0u : (uint32_t) (1 - s));
 }
 
-// Builds J[i] = first position >= tile_n reached from i (absolute exit), in shared memory.
-__device__ __forceinline__ void rle_dec_jump_closure(const uint8_t* __restrict__ xb, uint32_t tile0, uint32_t tile_n, uint16_t* Ja, uint16_t* Jb)
+// Builds J[i] = first position >= tile_n reached from i (absolute exit), in shared memory, by pointer doubling.
+// The loop stops as soon as every pointer is terminal: ceil(log2(tokens per tile)) + 1 rounds -- 3-4 on
+// literal-heavy data, up to 10 when the tile is all one-byte tokens. Returns the buffer holding the result.
+__device__ __forceinline__ uint16_t* rle_dec_jump_closure(const uint8_t* __restrict__ xb, uint32_t tile0, uint32_t tile_n, uint16_t* Ja, uint16_t* Jb)
 {
     for (uint32_t i = threadIdx.x; i < RD_TILE; i += RD_THREADS)
         Ja[i] = i < tile_n ? (uint16_t) (i + rle_tok_len(xb[tile0 + i])) : (uint16_t) i;
@@ -393,17 +395,20 @@ __device__ __forceinline__ void rle_dec_jump_closure(const uint8_t* __restrict__
     uint16_t *src = Ja, *dst = Jb;
     for (int r = 0; r < 10; ++r)
     {
+        bool open = false;
         for (uint32_t i = threadIdx.x; i < RD_TILE; i += RD_THREADS)
         {
             const uint16_t j = src[i];
-            dst[i]           = j < tile_n ? src[j] : j;
+            const uint16_t n = j < tile_n ? src[j] : j;
+            dst[i]           = n;
+            open |= n < tile_n;
         }
-        __syncthreads();
         uint16_t* tmp = src;
         src           = dst;
         dst           = tmp;
+        if (!__syncthreads_or(open)) break;
     }
-    // 10 swaps: result is back in Ja
+    return src;
 }
 
 __global__ void __launch_bounds__(RD_THREADS)
@@ -416,12 +421,12 @@ __global__ void __launch_bounds__(RD_THREADS)
     const uint32_t      tile0 = t * RD_TILE;
     if (tile0 >= r) return;
     const uint32_t tile_n = min((uint32_t) RD_TILE, r - tile0);
-    rle_dec_jump_closure(in + (uint64_t) b * stride, tile0, tile_n, Ja, Jb);
+    const uint16_t* J = rle_dec_jump_closure(in + (uint64_t) b * stride, tile0, tile_n, Ja, Jb);
     if (threadIdx.x < RD_ENTRIES)
     {
         // entries beyond the tile (only possible in a short last tile) are never followed
         const uint32_t e = threadIdx.x;
-        const uint32_t x = e < tile_n ? (uint32_t) Ja[e] - tile_n : 0u;
+        const uint32_t x = e < tile_n ? (uint32_t) J[e] - tile_n : 0u;
         t_exit[((uint64_t) b * tiles + t) * RD_ENTRIES + e] = (uint8_t) min(x, 255u);
     }
 }
@@ -466,16 +471,19 @@ __global__ void __launch_bounds__(RD_THREADS)
     uint16_t *src = Ja, *dst = Jb;
     for (int rd = 0; rd < 10; ++rd)
     {
+        bool open = false;
         for (uint32_t i = threadIdx.x; i < RD_TILE; i += RD_THREADS)
         {
             const uint16_t j = src[i];
             if (reach[i] && j < tile_n) reach[j] = 1;  // J^(2^rd) of a reachable start is reachable
-            dst[i] = j < tile_n ? src[j] : j;
+            const uint16_t n = j < tile_n ? src[j] : j;
+            dst[i]           = n;
+            open |= j < tile_n;  // this round still had a live pointer to follow
         }
-        __syncthreads();
         uint16_t* tmp = src;
         src           = dst;
         dst           = tmp;
+        if (!__syncthreads_or(open)) break;
     }
     // token bitmap + output count; truncated tokens are the reference's error exits (bra_rle.c:136,148)
     uint32_t mycnt = 0;
