@@ -148,6 +148,16 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
+    # stdout carries exactly one JSON line: anything libraries print meanwhile (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(json_fd, 1)
+        print(json.dumps(line), flush=True)
+
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -168,7 +178,7 @@ def main():
                 "dtype": "u8", "data": "synthetic", "config": config, "encode_gbs": r["encode_gbs"], "decode_gbs": r["decode_gbs"],
                 "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     import numpy as np
@@ -333,7 +343,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 if __name__ == "__main__":
