@@ -40,7 +40,7 @@ REFERENCE_API = [
 BATCH_API = [
     "bra_b200_device_count", "bra_b200_ctx_create", "bra_b200_ctx_destroy", "bra_b200_block_size", "bra_b200_max_batch",
     "bra_b200_payload_stride", "bra_b200_workspace_bytes", "bra_b200_last_stats", "bra_b200_encode_device", "bra_b200_decode_device",
-    "bra_b200_encode_bound", "bra_b200_encode_host", "bra_b200_decode_host", "bra_b200_gen_random", "bra_b200_gen_text",
+    "bra_b200_encode_bound", "bra_b200_encode_host", "bra_b200_decode_host", "bra_b200_list_host", "bra_b200_gen_random", "bra_b200_gen_text",
     "bra_b200_gen_periodic", "bra_b200_prof_enable", "bra_b200_prof_reset", "bra_b200_prof_count", "bra_b200_prof_read",
 ]
 
@@ -88,6 +88,8 @@ def lib() -> C.CDLL:
     L.bra_b200_encode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), u32p]
     L.bra_b200_decode_host.restype = C.c_int
     L.bra_b200_decode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), u32p]
+    L.bra_b200_list_host.restype = C.c_int
+    L.bra_b200_list_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.bra_b200_gen_random.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
     L.bra_b200_gen_text.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_char_p), C.c_uint32]
     L.bra_b200_gen_periodic.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
@@ -282,3 +284,13 @@ class Context:
         if rc != 0:
             raise RuntimeError(f"bra_b200_decode_host failed with code {rc}")
         return out[: osz.value], int(crc.value)
+
+    def list_host(self, stream_bytes) -> int:
+        """Plain size of a chunk stream, the reference's list mode (chunks.c:369-373): Huffman decode + RLE size pass only."""
+        n = int(stream_bytes.nbytes) if hasattr(stream_bytes, "nbytes") else int(stream_bytes.numel())
+        ptr = stream_bytes.ctypes.data if hasattr(stream_bytes, "ctypes") else stream_bytes.data_ptr()
+        osz = C.c_uint64(0)
+        rc = self.L.bra_b200_list_host(self.handle, ptr, n, C.byref(osz))
+        if rc != 0:
+            raise RuntimeError(f"bra_b200_list_host failed with code {rc}")
+        return int(osz.value)

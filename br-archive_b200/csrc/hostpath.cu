@@ -224,10 +224,11 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
     return 0;
 }
 
-extern "C" int bra_b200_decode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap, uint64_t* out_size,
-                                    uint32_t* crc_chain)
+// sizes_only: list mode of the reference (chunks.c:369-373) -- Huffman decode + RLE size pass, nothing is copied back
+static int decode_host_impl(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap, uint64_t* out_size,
+                            uint32_t* crc_chain, bool sizes_only)
 {
-    if (!c || !in || !out || !out_size)
+    if (!c || !in || (!out && !sizes_only) || !out_size)
     {
         bra_b200_log_error("bra_b200_decode_host: invalid arguments");
         return 1;
@@ -326,10 +327,25 @@ extern "C" int bra_b200_decode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
         if (i >= 2) cudaStreamWaitEvent(st, P.ev_out[slot], 0);  // output slot free once stage i-2 has been copied out
         const uint32_t gx = bra_div_up(267 + (uint64_t) sg.max_c, 4096);
         BRA_LAUNCH(P_GLUE, st, stream_scatter_kernel<<<dim3(gx, sg.nb), 256, 0, st>>>(d_str[slot], d_off[slot], d_hdr, d_pay, PS));
-        if (!decode_batch(c, d_hdr, d_pay, sg.nb, sg.max_r, sg.max_c, d_out[slot], d_len, d_crc, d_stat, st)) return 5;
+        if (!decode_batch(c, d_hdr, d_pay, sg.nb, sg.max_r, sg.max_c, d_out[slot], d_len, d_crc, d_stat, st, sizes_only)) return 5;
         if (!crc_headers(d_hdr, 268, sg.nb, d_hcrc, st)) return 5;
         if (cudaMemcpyAsync(h_misc.data(), d_len, (size_t) 4 * HB * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
         if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
+        if (sizes_only)
+        {
+            for (uint32_t b = 0; b < sg.nb; ++b)
+            {
+                if (h_misc[2 * (size_t) HB + b] != 0)
+                {
+                    bra_b200_log_error("bra_b200_list_host: chunk %u of the batch at offset %llu is corrupt", b, (unsigned long long) sg.pos);
+                    return 8;
+                }
+                produced += h_misc[b];
+            }
+            cudaEventRecord(P.ev_comp[slot], st);
+            cudaEventRecord(P.ev_out[slot], st);
+            continue;
+        }
         uint64_t o = 0;
         bool     contiguous = true;
         for (uint32_t b = 0; b < sg.nb; ++b)
@@ -376,6 +392,17 @@ extern "C" int bra_b200_decode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
     *out_size = produced;
     if (crc_chain) *crc_chain = crc;
     return 0;
+}
+
+extern "C" int bra_b200_decode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap, uint64_t* out_size,
+                                    uint32_t* crc_chain)
+{
+    return decode_host_impl(c, in, in_size, out, out_cap, out_size, crc_chain, false);
+}
+
+extern "C" int bra_b200_list_host(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_size, uint64_t* plain_size)
+{
+    return decode_host_impl(c, in, in_size, nullptr, 0, plain_size, nullptr, true);
 }
 
 // ---- synthetic workloads ------------------------------------------------------

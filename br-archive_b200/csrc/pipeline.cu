@@ -332,7 +332,7 @@ bool encode_batch(bra_b200_ctx* c, const uint8_t* d_in, uint32_t nb, uint32_t la
 }
 
 bool decode_batch(bra_b200_ctx* c, const uint8_t* d_hdr, const uint8_t* d_payload, uint32_t nb, uint32_t hint_r, uint32_t hint_c, uint8_t* d_out,
-                  uint32_t* d_out_len, uint32_t* d_crc, uint32_t* d_status, cudaStream_t st)
+                  uint32_t* d_out_len, uint32_t* d_crc, uint32_t* d_status, cudaStream_t st, bool sizes_only)
 {
     const uint32_t S = c->block;
     Arena          A = c->arena;
@@ -360,8 +360,19 @@ bool decode_batch(bra_b200_ctx* c, const uint8_t* d_hdr, const uint8_t* d_payloa
     RleDecArgs ra{};
     ra.d_in = w.R; ra.stride = c->rle_stride; ra.d_rlen = w.rlen; ra.max_r = max_r; ra.nblk = nb;
     ra.d_out = w.M; ra.out_stride = S; ra.out_cap = S; ra.d_nlen = w.nlen; ra.d_err = w.err;
-    ra.d_t_exit = w.t_exit; ra.d_t_entry = w.t_entry; ra.d_t_tok = w.t_tok; ra.d_t_ocnt = w.t_ocnt; ra.size_only = false;
+    ra.d_t_exit = w.t_exit; ra.d_t_entry = w.t_entry; ra.d_t_tok = w.t_tok; ra.d_t_ocnt = w.t_ocnt; ra.size_only = sizes_only;
     BRA_CUDA_TRY(cudaMemsetAsync(w.nlen, 0, nb * 4, st));
+    if (sizes_only)
+    {
+        // list mode (reference chunks.c:369-373): Huffman decode, then bra_rle_decode_compute_size only. A chunk whose
+        // Huffman stream is broken fails; one whose RLE tokens are truncated counts as 0 bytes, as in the reference.
+        BRA_CUDA_TRY(cudaMemcpyAsync(d_status, w.err, nb * 4, cudaMemcpyDeviceToDevice, st));
+        if (!rle_decode_batch(ra, st)) return false;
+        BRA_CUDA_TRY(cudaMemcpyAsync(d_out_len, w.nlen, nb * 4, cudaMemcpyDeviceToDevice, st));
+        BRA_CUDA_TRY(cudaMemsetAsync(d_crc, 0, nb * 4, st));
+        BRA_CUDA_TRY(cudaGetLastError());
+        return true;
+    }
     if (!rle_decode_batch(ra, st)) return false;
     BRA_LAUNCH(P_GLUE, st, post_rle_kernel<<<bra_div_up(nb, 128), 128, 0, st>>>(w.nlen, w.primary, w.err, nb));
 
@@ -425,7 +436,7 @@ extern "C" int bra_b200_decode_device(bra_b200_ctx_t* c, const uint8_t* d_hdr, c
     {
         const uint32_t nb = std::min(c->max_batch, nblk - b0);
         if (!decode_batch(c, d_hdr + (uint64_t) b0 * 268, d_payload + (uint64_t) b0 * c->pay_stride, nb, hint_max_r, hint_max_c,
-                          d_out + (uint64_t) b0 * c->block, d_out_len + b0, d_crc_raw + b0, d_status + b0, st))
+                          d_out + (uint64_t) b0 * c->block, d_out_len + b0, d_crc_raw + b0, d_status + b0, st, false))
             return 3;
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) return 4;

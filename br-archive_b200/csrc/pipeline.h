@@ -11,7 +11,7 @@ uint64_t pay_stride_for(uint32_t block);
 bool encode_batch(bra_b200_ctx* c, const uint8_t* d_in, uint32_t nb, uint32_t last_len, uint8_t* d_hdr, uint8_t* d_payload, uint32_t* d_crc,
                   cudaStream_t st);
 bool decode_batch(bra_b200_ctx* c, const uint8_t* d_hdr, const uint8_t* d_payload, uint32_t nb, uint32_t hint_r, uint32_t hint_c, uint8_t* d_out,
-                  uint32_t* d_out_len, uint32_t* d_crc, uint32_t* d_status, cudaStream_t st);
+                  uint32_t* d_out_len, uint32_t* d_crc, uint32_t* d_status, cudaStream_t st, bool sizes_only);
 // device staging buffer of the context for the host path (grown on demand)
 uint8_t* ctx_io_buffer(bra_b200_ctx* c, uint64_t bytes);
 cudaStream_t ctx_stream(bra_b200_ctx* c);

@@ -244,8 +244,8 @@ bool bra_io_file_chunks_decompress_file(bra_io_file_t* dst, bra_io_file_t* src, 
     if (dst != NULL && (dst->f == NULL || dst->fn == NULL)) goto fail;
     const uint64_t stream_cap = data_size < max_stream ? (data_size ? data_size : 1) : max_stream;
     stream = malloc(stream_cap);
-    plain  = malloc((size_t) _bra_min((uint64_t) B200_WINDOW_CHUNKS, data_size / BRA_IO_CHUNK_HEADER_SIZE + 1) * BRA_MAX_CHUNK_SIZE);
-    if (stream == NULL || plain == NULL) goto fail;
+    if (decode) plain = malloc((size_t) _bra_min((uint64_t) B200_WINDOW_CHUNKS, data_size / BRA_IO_CHUNK_HEADER_SIZE + 1) * BRA_MAX_CHUNK_SIZE);
+    if (stream == NULL || (decode && plain == NULL)) goto fail;
 
     for (uint64_t i = 0; i < data_size;)
     {
@@ -283,8 +283,11 @@ bool bra_io_file_chunks_decompress_file(bra_io_file_t* dst, bra_io_file_t* src, 
         }
         uint64_t plain_size = 0;
         uint32_t crc        = decode ? me->crc32 : 0;
-        /* huffman, rle, mtf, bwt decode of every chunk + CRC chain of chunks.c:396-397 */
-        if (bra_b200_decode_host(ctx, stream, w, plain, (uint64_t) n * BRA_MAX_CHUNK_SIZE, &plain_size, &crc) != 0)
+        /* list mode (chunks.c:369-373): huffman decode + rle size only;
+         * otherwise huffman, rle, mtf, bwt decode of every chunk + CRC chain of chunks.c:396-397 */
+        const int rc = decode ? bra_b200_decode_host(ctx, stream, w, plain, (uint64_t) n * BRA_MAX_CHUNK_SIZE, &plain_size, &crc)
+                              : bra_b200_list_host(ctx, stream, w, &plain_size);
+        if (rc != 0)
         {
             bra_log_error("unable to decode chunks of file: %s ", src->fn);
             goto fail;

@@ -79,6 +79,11 @@ int bra_b200_encode_host(bra_b200_ctx_t* ctx, const uint8_t* in, uint64_t total,
  * reference chunks.c:396-397 does. out_cap must hold the decoded data. */
 int bra_b200_decode_host(bra_b200_ctx_t* ctx, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap, uint64_t* out_size,
                          uint32_t* crc_chain);
+/* List mode (reference chunks.c:369-373, `decode == false`): Huffman-decode every chunk of the stream and
+ * sum bra_rle_decode_compute_size over them into *plain_size. No MTF/BWT stage runs and nothing but the
+ * sizes comes back. As in the reference, a broken Huffman stream fails the call; a truncated RLE token
+ * makes its chunk count as 0 bytes. */
+int bra_b200_list_host(bra_b200_ctx_t* ctx, const uint8_t* in, uint64_t in_size, uint64_t* plain_size);
 
 /* ---- launch accounting (process-wide; used by bench.py for `gpu_launches` and the roofline) ----
  * Every kernel launch of the library is counted per kernel family. With timing enabled each launch is

@@ -264,6 +264,7 @@ def _check_batch(pkg, oracle, data: bytes, block: int, max_batch: int, full_comp
         assert chain == exp_chain
         plain, chain2 = ctx.decode_host(stream, n)
         assert plain.tobytes() == data and chain2 == exp_chain
+        assert ctx.list_host(stream) == n  # list mode: Huffman decode + RLE size pass only
         return ctx.stats()
     finally:
         ctx.close()
@@ -339,6 +340,33 @@ def test_decode_rejects_corrupt_blocks(pkg, oracle, vocab):
         s = status.cpu().numpy()
         assert s[0] == 0 and s[3] == 0 and s[1] != 0 and s[2] != 0
         assert out.cpu().numpy()[:block].tobytes() == data[:block]
+    finally:
+        ctx.close()
+
+
+def test_list_mode_sizes_follow_the_reference(pkg, oracle, vocab):
+    """Reference chunks.c:369-373 (`unbra -l`): per chunk huffman-decode, then bra_rle_decode_compute_size. The primary
+    index is not looked at, a truncated RLE token makes the chunk count as 0 bytes, a broken Huffman stream fails."""
+    block = 16384
+
+    def chunk(rle: bytes, primary=0):
+        lengths, payload = oracle.huffman_encode(rle)
+        return primary.to_bytes(3, "little") + lengths + len(rle).to_bytes(4, "little") + len(payload).to_bytes(4, "little") + payload
+
+    good = oracle.rle_encode(oracle.mtf_encode(oracle.bwt_encode(_text(pkg, vocab, block))[0]))
+    runs = bytes([0x81, 65]) * 40                       # 40 runs of 128 x 'A' = 5120 bytes
+    truncated = bytes([5, 1, 2, 3]) + bytes([0x81])     # literal of 6 with 3 bytes present, then a run without its byte
+    assert oracle.rle_decode_size(good) == block and oracle.rle_decode_size(runs) == 5120 and oracle.rle_decode_size(truncated) == 0
+    ctx = pkg.Context(0, block, 8)
+    try:
+        stream = chunk(good) + chunk(runs, primary=6000) + chunk(truncated) + chunk(good)
+        assert ctx.list_host(np.frombuffer(stream, dtype=np.uint8)) == block + 5120 + 0 + block
+        with pytest.raises(RuntimeError):  # the full decode does check the primary index and the RLE tokens (chunks.c:376-389)
+            ctx.decode_host(np.frombuffer(stream, dtype=np.uint8), 4 * block)
+        bad = bytearray(chunk(good))
+        bad[3:3 + 256] = bytes([1]) * 256               # every symbol with a 1-bit code: no such tree (bra_huffman.c:294-303)
+        with pytest.raises(RuntimeError):
+            ctx.list_host(np.frombuffer(bytes(bad), dtype=np.uint8))
     finally:
         ctx.close()
 
