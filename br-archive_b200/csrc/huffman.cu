@@ -274,6 +274,10 @@ struct HdShared
     bra_huf_dec_t tab;
     uint16_t      lut[1 << HD_LUT_BITS];  // (sym << 8) | len for codes of at most HD_LUT_BITS bits, 0 = longer / invalid
     uint32_t      start[HD_THREADS + 1];  // bit offset (relative to the sequence start) of the first codeword of each subsequence
+    uint32_t      used[HD_THREADS];       // sync kernel: start value each subsequence was last walked from
+    uint16_t      count[HD_THREADS];      // sync kernel: codewords that start inside each subsequence
+    uint16_t      list[HD_THREADS];       // sync kernel: subsequences to walk this round, compacted
+    uint32_t      wcnt[HD_THREADS / 32];
     uint32_t      red[34];
 };
 
@@ -436,36 +440,52 @@ __global__ void __launch_bounds__(HD_THREADS)
     }
     __syncthreads();
 
-    uint32_t used  = 0xFFFFFFFFu;  // start value my current (exit, count) were computed from
-    uint32_t myexit = 0, mycount = 0;
+    // Jacobi iteration on the subsequence starts. Only subsequences whose start moved are walked again, and on
+    // data that re-synchronises slowly (near-uniform code lengths) those are a few scattered ones per round: they
+    // are compacted so that the walks run on dense warps instead of one or two lanes in each of the eight.
+    S.used[k]  = 0xFFFFFFFFu;  // start value the current (exit, count) of subsequence k were computed from
+    S.count[k] = 0;
     if (!first_run && k != 0)
     {
-        // state from the previous launch is still valid unless my start changes
-        used    = S.start[k];
-        myexit  = S.start[k + 1];
-        mycount = sub_count[sub_idx];
+        // state from the previous launch is still valid unless the start changes
+        S.used[k]  = S.start[k];
+        S.count[k] = sub_count[sub_idx];
     }
+    __syncthreads();
     for (int it = 0; it < HD_THREADS + 2; ++it)
     {
-        const uint32_t st = S.start[k];
-        bool           ch = false;
-        uint32_t       nx = myexit;
-        if (st != used)
+        const bool     need = S.start[k] != S.used[k];
+        const uint32_t ball = __ballot_sync(BRA_FULL, need);
+        if (lane_id() == 0) S.wcnt[warp_id()] = __popc(ball);
+        __syncthreads();
+        uint32_t before = 0, nact = 0;
+#pragma unroll
+        for (uint32_t w = 0; w < HD_THREADS / 32; ++w)
         {
-            bool dead;
-            nx   = hd_walk(S, st, (k + 1) * HD_SUB_BITS, data_end, &mycount, &dead);
-            if (dead || nx < (k + 1) * HD_SUB_BITS) nx = (k + 1) * HD_SUB_BITS;  // dead path / payload ended: neutral guess
-            used   = st;
-            myexit = nx;
+            const uint32_t c = S.wcnt[w];
+            before += w < warp_id() ? c : 0u;
+            nact += c;
+        }
+        if (nact == 0) break;
+        if (need) S.list[before + __popc(ball & lanemask_lt())] = (uint16_t) k;
+        __syncthreads();
+        uint32_t j = 0, nx = 0;
+        if (k < nact)
+        {
+            j                 = S.list[k];
+            const uint32_t st = S.start[j];
+            uint32_t       cnt;
+            bool           dead;
+            nx = hd_walk(S, st, (j + 1) * HD_SUB_BITS, data_end, &cnt, &dead);
+            if (dead || nx < (j + 1) * HD_SUB_BITS) nx = (j + 1) * HD_SUB_BITS;  // dead path / payload ended: neutral guess
+            S.used[j]  = st;
+            S.count[j] = (uint16_t) cnt;
         }
         __syncthreads();
-        if (S.start[k + 1] != nx)
-        {
-            S.start[k + 1] = nx;
-            ch             = true;
-        }
-        if (!__syncthreads_or(ch)) break;
+        if (k < nact) S.start[j + 1] = nx;
+        __syncthreads();
     }
+    const uint32_t mycount = S.count[k];
     sub_start[sub_idx] = (uint8_t) (S.start[k] - k * HD_SUB_BITS);
     sub_count[sub_idx] = (uint16_t) mycount;
     uint32_t total;

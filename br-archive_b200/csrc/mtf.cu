@@ -8,12 +8,13 @@
 //               decode -> the permutation of list positions the segment's ranks perform
 //   scan    : per block, compose the summaries left to right -> the list entering each segment
 //   apply   : replay each segment from its entry list.
-// Replay is one segment per THREAD: each lane owns a 256-byte list in shared memory (stride 65
-// eight-byte words, so lanes working at the same depth hit different banks) and does what the reference
-// does -- find / shift -- but eight list entries per shared-memory word. A warp therefore advances
-// 32 segments at once, and the cost per symbol is (rank/8 + 1) word steps of the slowest lane:
-// about one warp instruction per symbol on BWT output (ranks are small), ~20 on uniform random
-// ranks. Traffic: read n + write n (+ 256 B of state per 4 KiB segment, twice). Issue/latency bound.
+// Replay is one segment per THREAD: each lane owns a 256-byte list in shared memory (stride 17
+// sixteen-byte words, so lanes working at the same depth hit different bank groups) and does what the
+// reference does -- find / shift -- but sixteen list entries per shared-memory access. A warp therefore
+// advances 32 segments at once, and the cost per symbol is (rank/16 + 1) chunk steps of the slowest lane:
+// a few warp instructions per symbol on BWT output (ranks are small), the instruction count of ~16 chunk
+// steps on uniform random ranks. Traffic: read n + write n (+ 256 B of state per 4 KiB segment, twice).
+// Issue bound.
 #include "bra_common.cuh"
 #include "bra_kernels.h"
 
@@ -22,53 +23,76 @@ namespace bra {
 #define MTF_SEG 4096
 #define MTF_WARPS 4          // warps per CTA in the warp-per-segment summary kernel
 #define MTF_LANE_WARPS 4     // warps per CTA in the lane-per-segment replay kernels
-#define MTF_LIST_QW 33       // 32 eight-byte words of list + 1 pad: lane stride 33 -> lanes at the same depth use distinct banks
+#define MTF_LIST_V4 17       // 16 sixteen-byte words of list + 1 pad: odd lane stride -> lanes at the same depth use distinct bank groups
 
 // ---- per-lane list in shared memory -----------------------------------------------------------------
-// Q[0..31]: entry k lives in byte (k & 7) of the 64-bit word (k >> 3).
+// Q[0..15]: entry k is byte k of the 256-byte array (little endian inside each 32-bit word). Moving an entry to
+// the front shifts everything before it up by one byte: one 128-bit load, four byte-permutes and one 128-bit
+// store per sixteen entries (the instruction count is what bounds this kernel on high ranks, not HBM).
+
+// (cur << 8) | (prev >> 24): the image of one 32-bit word after the shift
+__device__ __forceinline__ uint32_t mtf_shift_word(uint32_t prev, uint32_t cur) { return __byte_perm(prev, cur, 0x6543); }
+
+__device__ __forceinline__ uint4 mtf_shift_chunk(uint32_t prev, const uint4 v)
+{
+    return make_uint4(mtf_shift_word(prev, v.x), mtf_shift_word(v.x, v.y), mtf_shift_word(v.y, v.z), mtf_shift_word(v.z, v.w));
+}
+
+// the chunk that holds the moved entry at byte o: bytes <= o take the shifted image, the others stay
+__device__ __forceinline__ uint4 mtf_merge_chunk(const uint4 v, const uint4 n, uint32_t o)
+{
+    const uint32_t wo = o >> 2;
+    const uint32_t pm = 0xFFFFFFFFu >> ((3u - (o & 3u)) * 8u);  // bytes 0..(o&3) of the word that holds the entry
+    const uint32_t mx = wo > 0 ? 0xFFFFFFFFu : pm;
+    const uint32_t my = wo > 1 ? 0xFFFFFFFFu : (wo == 1 ? pm : 0u);
+    const uint32_t mz = wo > 2 ? 0xFFFFFFFFu : (wo == 2 ? pm : 0u);
+    const uint32_t mw = wo == 3 ? pm : 0u;
+    return make_uint4((n.x & mx) | (v.x & ~mx), (n.y & my) | (v.y & ~my), (n.z & mz) | (v.z & ~mz), (n.w & mw) | (v.w & ~mw));
+}
 
 // decode one rank: returns the symbol at position r and moves it to the front
-__device__ __forceinline__ uint32_t lane_mtf_decode(uint64_t* Q, uint32_t r)
+__device__ __forceinline__ uint32_t lane_mtf_decode(uint4* Q, uint32_t r)
 {
-    const uint32_t wr = r >> 3, br = r & 7u;
-    uint64_t       cur = Q[wr];
-    const uint32_t sym = (uint32_t) (cur >> (br * 8)) & 0xFFu;
+    const uint32_t sym = reinterpret_cast<const uint8_t*>(Q)[r];
     if (r == 0) return sym;
-    uint64_t       below    = wr ? Q[wr - 1] : 0ull;
-    uint64_t       incoming = wr ? (below >> 56) : (uint64_t) sym;
-    const uint64_t mask     = br == 7 ? ~0ull : ((1ull << ((br + 1) * 8)) - 1ull);  // bytes <= br take the shifted image
-    Q[wr] = (((cur << 8) | incoming) & mask) | (cur & ~mask);
-    for (int w = (int) wr - 1; w >= 0; --w)
+    const uint32_t nq   = r >> 4;
+    uint32_t       prev = sym << 24;  // byte entering the next word from below
+    for (uint32_t q = 0; q < nq; ++q)
     {
-        cur      = below;
-        below    = w ? Q[w - 1] : 0ull;
-        incoming = w ? (below >> 56) : (uint64_t) sym;
-        Q[w]     = (cur << 8) | incoming;
+        const uint4 v = Q[q];
+        Q[q]          = mtf_shift_chunk(prev, v);
+        prev          = v.w;
     }
+    const uint4 v = Q[nq];
+    Q[nq]         = mtf_merge_chunk(v, mtf_shift_chunk(prev, v), r & 15u);
     return sym;
 }
 
+// first zero byte of t flagged in bit 7 of that byte (higher flags may be spurious, the lowest one never is)
+__device__ __forceinline__ uint32_t mtf_zero_bytes(uint32_t t) { return (t - 0x01010101u) & ~t & 0x80808080u; }
+
 // encode one symbol: returns its position and moves it to the front (single forward pass)
-__device__ __forceinline__ uint32_t lane_mtf_encode(uint64_t* Q, uint32_t x)
+__device__ __forceinline__ uint32_t lane_mtf_encode(uint4* Q, uint32_t x)
 {
-    const uint64_t x8    = (uint64_t) x * 0x0101010101010101ull;
-    uint64_t       carry = x;  // byte entering the next word from below
-    for (uint32_t w = 0;; ++w)
+    const uint32_t x4   = x * 0x01010101u;
+    uint32_t       prev = x << 24;
+    for (uint32_t q = 0;; ++q)
     {
-        const uint64_t cur = Q[w];
-        const uint64_t t   = cur ^ x8;
-        const uint64_t z   = (t - 0x0101010101010101ull) & ~t & 0x8080808080808080ull;  // lowest marker = first byte equal to x
-        if (z == 0)
+        const uint4    v  = Q[q];
+        const uint32_t z0 = mtf_zero_bytes(v.x ^ x4), z1 = mtf_zero_bytes(v.y ^ x4), z2 = mtf_zero_bytes(v.z ^ x4), z3 = mtf_zero_bytes(v.w ^ x4);
+        const uint4    n  = mtf_shift_chunk(prev, v);
+        if ((z0 | z1 | z2 | z3) == 0)
         {
-            Q[w]  = (cur << 8) | carry;
-            carry = cur >> 56;
+            Q[q] = n;
+            prev = v.w;
             continue;
         }
-        const uint32_t b = (uint32_t) (__ffsll((long long) z) - 1) >> 3;
-        if (w == 0 && b == 0) return 0;  // already in front
-        const uint64_t mask = b == 7 ? ~0ull : ((1ull << ((b + 1) * 8)) - 1ull);
-        Q[w] = (((cur << 8) | carry) & mask) | (cur & ~mask);
-        return w * 8 + b;
+        const uint32_t wo = z0 ? 0u : (z1 ? 1u : (z2 ? 2u : 3u));
+        const uint32_t z  = z0 ? z0 : (z1 ? z1 : (z2 ? z2 : z3));
+        const uint32_t o  = wo * 4 + ((uint32_t) (__ffs((int) z) - 1) >> 3);
+        if (q == 0 && o == 0) return 0;  // already in front
+        Q[q] = mtf_merge_chunk(v, n, o);
+        return q * 16 + o;
     }
 }
 
@@ -83,30 +107,29 @@ __global__ void __launch_bounds__(MTF_LANE_WARPS * 32)
     mtf_lane_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t stride, const uint32_t* __restrict__ len, uint32_t segs,
                     const uint8_t* __restrict__ state_in, uint8_t* __restrict__ summ_out)
 {
-    __shared__ uint64_t s_list[MTF_LANE_WARPS * 32 * MTF_LIST_QW];
+    __shared__ uint4 s_list[MTF_LANE_WARPS * 32 * MTF_LIST_V4];
     const uint32_t b   = blockIdx.y;
     const uint32_t n   = len[b];
     const uint32_t seg = blockIdx.x * (MTF_LANE_WARPS * 32) + threadIdx.x;
     if ((uint64_t) seg * MTF_SEG >= n) return;  // no barriers below: lanes are independent
     const uint32_t m   = min((uint32_t) MTF_SEG, n - seg * MTF_SEG);
     const uint64_t off = (uint64_t) b * stride + (uint64_t) seg * MTF_SEG;
-    uint64_t*      W   = s_list + threadIdx.x * MTF_LIST_QW;
+    uint4*         W   = s_list + threadIdx.x * MTF_LIST_V4;
 
     if (MODE == 2)
     {
-#pragma unroll 8
-        for (uint32_t w = 0; w < 32; ++w) W[w] = 0x0706050403020100ull + (uint64_t) (w * 8) * 0x0101010101010101ull;
+#pragma unroll 4
+        for (uint32_t q = 0; q < 16; ++q)
+        {
+            const uint32_t w0 = 0x03020100u + (q * 16) * 0x01010101u;
+            W[q]              = make_uint4(w0, w0 + 0x04040404u, w0 + 0x08080808u, w0 + 0x0C0C0C0Cu);
+        }
     }
     else
     {
         const uint4* st = reinterpret_cast<const uint4*>(state_in + ((uint64_t) b * segs + seg) * 256);
 #pragma unroll 4
-        for (uint32_t q = 0; q < 16; ++q)
-        {
-            const uint4 v = st[q];
-            W[q * 2 + 0]  = ((uint64_t) v.y << 32) | v.x;
-            W[q * 2 + 1]  = ((uint64_t) v.w << 32) | v.z;
-        }
+        for (uint32_t q = 0; q < 16; ++q) W[q] = st[q];
     }
 
     const uint8_t* ip = in + off;
@@ -114,23 +137,27 @@ __global__ void __launch_bounds__(MTF_LANE_WARPS * 32)
     uint32_t       i  = 0;
     for (; i + 16 <= m; i += 16)
     {
-        const uint4    v     = *reinterpret_cast<const uint4*>(ip + i);
-        const uint32_t iw[4] = {v.x, v.y, v.z, v.w};
-        uint32_t       ow[4];
-#pragma unroll
+        const uint4 v = *reinterpret_cast<const uint4*>(ip + i);
+        uint4       ov;
+        // four symbols per trip, the trip not unrolled: the replay code is long and sixteen copies of it overflow the instruction cache
+#pragma unroll 1
         for (int q = 0; q < 4; ++q)
         {
-            uint32_t o = 0;
+            const uint32_t iw = q == 0 ? v.x : (q == 1 ? v.y : (q == 2 ? v.z : v.w));
+            uint32_t       o  = 0;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
             {
-                const uint32_t x = (iw[q] >> (k * 8)) & 0xFFu;
+                const uint32_t x = (iw >> (k * 8)) & 0xFFu;
                 const uint32_t r = (MODE == 0) ? lane_mtf_encode(W, x) : lane_mtf_decode(W, x);
                 o |= r << (k * 8);
             }
-            ow[q] = o;
+            if (q == 0) ov.x = o;
+            else if (q == 1) ov.y = o;
+            else if (q == 2) ov.z = o;
+            else ov.w = o;
         }
-        *reinterpret_cast<uint4*>(op + i) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        *reinterpret_cast<uint4*>(op + i) = ov;
     }
     for (; i < m; ++i)
     {
@@ -142,8 +169,7 @@ __global__ void __launch_bounds__(MTF_LANE_WARPS * 32)
     {
         uint4* so = reinterpret_cast<uint4*>(summ_out + ((uint64_t) b * segs + seg) * 256);
 #pragma unroll 4
-        for (uint32_t q = 0; q < 16; ++q)
-            so[q] = make_uint4((uint32_t) W[q * 2], (uint32_t) (W[q * 2] >> 32), (uint32_t) W[q * 2 + 1], (uint32_t) (W[q * 2 + 1] >> 32));
+        for (uint32_t q = 0; q < 16; ++q) so[q] = W[q];
     }
 }
 
