@@ -825,12 +825,27 @@ __global__ void __launch_bounds__(IB_THREADS)
     uint32_t idx = (w == K) ? primary[b] : w * R;
     if (q >= n)
     {
-        for (uint32_t t = 0; t < steps; ++t)
+        // a walk's bytes are consecutive: gather four into one aligned 32-bit store (a byte store costs a whole L2 transaction)
+        const uint32_t m   = min(steps, n - min(n, o0));
+        uint32_t       acc = 0, nacc = 0;
+        for (uint32_t t = 0; t < m; ++t)
         {
             const uint32_t e = Wb[idx];
-            if (o0 + t < n) ob[o0 + t] = (uint8_t) e;
-            idx = e >> 8;
+            idx              = e >> 8;
+            acc |= (e & 0xFFu) << (8u * nacc);
+            ++nacc;
+            const uint32_t o = o0 + t + 1;  // bytes [o - nacc, o) are pending
+            if (((reinterpret_cast<uintptr_t>(ob) + o) & 3u) == 0)
+            {
+                if (nacc == 4)
+                    *reinterpret_cast<uint32_t*>(ob + o - 4) = acc;
+                else
+                    for (uint32_t i = 0; i < nacc; ++i) ob[o - nacc + i] = (uint8_t) (acc >> (8u * i));
+                acc  = 0;
+                nacc = 0;
+            }
         }
+        for (uint32_t i = 0; i < nacc; ++i) ob[o0 + m - nacc + i] = (uint8_t) (acc >> (8u * i));
     }
     else
     {

@@ -567,7 +567,9 @@ __global__ void __launch_bounds__(HD_THREADS)
     if (!(pos < sub_end && pos < data_end && o < orig)) return;
     HdReader R;
     hd_open(S, R, pos);
-    // same walk as hd_walk (so the counts agree), now storing the symbols
+    // same walk as hd_walk (so the counts agree), now storing the symbols: four at a time as one aligned
+    // 32-bit store wherever the output position allows it (byte stores cost one L2 transaction each)
+    uint32_t acc = 0, nacc = 0;  // symbols not stored yet: they belong to ob[o - nacc .. o)
     while (pos < sub_end && pos < data_end && o < orig)
     {
         uint8_t        sym = 0;
@@ -578,11 +580,23 @@ __global__ void __launch_bounds__(HD_THREADS)
             break;
         }
         if (pos + l > data_end) break;
-        ob[o++] = sym;
+        acc |= (uint32_t) sym << (8u * nacc);
+        ++nacc;
+        ++o;
+        if (((reinterpret_cast<uintptr_t>(ob) + o) & 3u) == 0)
+        {
+            if (nacc == 4)
+                *reinterpret_cast<uint32_t*>(ob + o - 4) = acc;
+            else
+                for (uint32_t i = 0; i < nacc; ++i) ob[o - nacc + i] = (uint8_t) (acc >> (8u * i));
+            acc  = 0;
+            nacc = 0;
+        }
         hd_skip(S, R, l);
         pos += l;
         if (o == orig) end_bit[b] = seq * HD_SEQ_BITS + pos;
     }
+    for (uint32_t i = 0; i < nacc; ++i) ob[o - nacc + i] = (uint8_t) (acc >> (8u * i));
 }
 
 // Bytes after the one holding the last symbol: the reference keeps walking them from the tree root
