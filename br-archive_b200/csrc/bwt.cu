@@ -402,6 +402,24 @@ __device__ __forceinline__ int rot_cmp_window(const uint8_t* __restrict__ T, uin
     uint32_t ia = a + from, ic = c + from;
     if (ia >= p) ia -= p;
     if (ic >= p) ic -= p;
+    if (ia + FIN_DEPTH + 4u <= p && ic + FIN_DEPTH + 4u <= p)
+    {
+        // neither window wraps: stream aligned words, one new word per side and step (T is 16-byte aligned)
+        const uint32_t* Ta = reinterpret_cast<const uint32_t*>(T) + (ia >> 2);
+        const uint32_t* Tc = reinterpret_cast<const uint32_t*>(T) + (ic >> 2);
+        const uint32_t  sa = (ia & 3u) * 8u, sc = (ic & 3u) * 8u;
+        uint32_t        a0 = Ta[0], c0 = Tc[0];
+#pragma unroll 4
+        for (uint32_t k = 1; k <= FIN_DEPTH / 4u; ++k)
+        {
+            const uint32_t a1 = Ta[k], c1 = Tc[k];
+            const uint32_t x = __funnelshift_r(a0, a1, sa), y = __funnelshift_r(c0, c1, sc);  // bytes in memory order, first byte lowest
+            if (x != y) return __byte_perm(x, 0, 0x0123) < __byte_perm(y, 0, 0x0123) ? -1 : 1;
+            a0 = a1;
+            c0 = c1;
+        }
+        return 0;
+    }
     uint32_t k = 0;
     while (k < FIN_DEPTH)
     {
