@@ -259,19 +259,34 @@ def main():
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    e2e_enc_s = 0.0
     for _ in range(e2e_steps):
-        stream, chain = ctx.encode_host(host, out=stream_buf)
+        t1 = time.perf_counter()
+        stream, chain = ctx.encode_host(host, out=stream_buf)   # returns when the stream is complete in host memory
+        e2e_enc_s += time.perf_counter() - t1
         plain, chain2 = ctx.decode_host(stream, nbytes, out=plain_buf)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    e2e_enc_s /= e2e_steps
     assert chain == chain2 and torch.equal(plain_buf, host), "end-to-end round trip mismatch"
     stream_bytes = int(stream.numel())
+    # pinned-memory copy rates of this box, to read the end-to-end figure against (outside every timed region)
+    pc = []
+    for src, dst in ((host, d_in), (d_in, plain_buf)):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0.record()
+        dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        pc.append(nbytes / (e0.elapsed_time(e1) / 1e3) / 1e9)
 
     # ---- reduce over ranks: max time, summed bytes ---------------------------------------------------------
-    t = torch.tensor([total_ms, enc_ms, dec_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, enc_ms, dec_ms, e2e_s * 1e3, e2e_enc_s * 1e3, (e2e_s - e2e_enc_s) * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, enc_ms, dec_ms, e2e_ms = [float(x) for x in t.tolist()]
+    total_ms, enc_ms, dec_ms, e2e_ms, e2e_enc_ms, e2e_dec_ms = [float(x) for x in t.tolist()]
     job_bytes = nbytes * world
     value = job_bytes * args.steps / (total_ms / 1e3) / 1e9
 
@@ -329,7 +344,9 @@ def main():
                 "huffman_sync_sweeps": stats["huf_sweeps"],
                 "clocks": clocks,
                 "e2e": {"value": job_bytes / (e2e_ms / 1e3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": nbytes + stream_bytes,
-                        "d2h_bytes_per_step": stream_bytes + nbytes, "api": "bra_b200_encode_host + bra_b200_decode_host (pinned host buffers)"},
+                        "d2h_bytes_per_step": stream_bytes + nbytes, "api": "bra_b200_encode_host + bra_b200_decode_host (pinned host buffers)",
+                        "encode_gbs": job_bytes / (e2e_enc_ms / 1e3) / 1e9, "decode_gbs": job_bytes / (e2e_dec_ms / 1e3) / 1e9,
+                        "pinned_copy_gbs": {"h2d": pc[0], "d2h": pc[1]}},
                 "gpu_launches": sum(n for n, _ in prof.values()),
                 "kernel_ms": {k: round(v[1] / args.steps, 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1]) if v[0]},
                 "roofline": roof, "chain_roofline": chain_roof}

@@ -39,6 +39,10 @@ bool crc_headers(const uint8_t* d_hdr, uint32_t item_bytes, uint32_t nitems, uin
 
 // ---- sort.cu ------------------------------------------------------------------------------
 size_t radix_hist_bytes(uint32_t max_len, uint32_t nblk);
+// small host <-> device transfers done by a copy kernel through pinned, device-visible host memory: a cudaMemcpyAsync of
+// a few bytes would wait on its copy engine behind the bulk copies of the neighbouring pipeline stages
+bool mail_fetch(uint32_t* d_dst, const uint32_t* h_src, uint32_t words, cudaStream_t st);
+bool mail_publish(uint32_t* h_dst, const uint32_t* d_src, uint32_t words, cudaStream_t st);
 bool   radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t stride,
                       const uint32_t* d_len, const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t bits, bool hist_ready,
                       uint32_t* d_hist, cudaStream_t st);
@@ -68,6 +72,10 @@ struct BwtFwdArgs
     uint8_t*  d_bad;
     uint32_t  bad_stride;
     uint32_t* h_rounds;  // optional: number of doubling rounds executed
+    // optional pinned, device-visible host words: [0,2) loop status, [2,2+div_cap) divisor values, then nblk offsets and
+    // nblk counts. With it the loop's small transfers are done by copy kernels and do not queue behind bulk copies
+    // on the copy engines; without it they are plain cudaMemcpyAsync calls.
+    uint32_t* h_mail;
 };
 bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st);
 
@@ -168,6 +176,7 @@ struct HufDecArgs
     uint32_t *      d_seq_entry, *d_seq_exit, *d_seq_count;  // nblk*seqs
     uint32_t *      d_end_bit, *d_changed;
     uint32_t*       h_sweeps;
+    uint32_t*       h_mail;  // optional pinned, device-visible host word for the sweep status (see BwtFwdArgs::h_mail)
 };
 bool     huf_decode_batch(const HufDecArgs& a, cudaStream_t st);
 uint32_t huf_dec_seqs(uint32_t max_c);

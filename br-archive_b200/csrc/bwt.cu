@@ -23,6 +23,8 @@
 #include "bra_common.cuh"
 #include "bra_kernels.h"
 
+#include <string.h>
+
 #include <algorithm>
 #include <utility>
 #include <vector>
@@ -443,11 +445,19 @@ __device__ __forceinline__ int rot_cmp_window(const uint8_t* __restrict__ T, uin
     return 0;
 }
 
+// Slots that are singleton groups already (most of them) are copied through; the members of the remaining
+// groups are first compacted into a shared-memory list, so that the comparison loops run on full warps
+// instead of on the few lanes of each warp that happen to sit in a group. (Spreading the comparisons
+// evenly as (member, other member) work items was measured too: the bookkeeping costs what the balance gains.)
 __global__ void __launch_bounds__(EW_THREADS)
     bwt_finish_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip,
                       uint32_t h, const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags_old, uint32_t* __restrict__ sa_out,
                       uint8_t* __restrict__ flags_new, int* __restrict__ tile_last, uint32_t tiles, uint32_t* __restrict__ ngroups)
 {
+    __shared__ uint16_t s_list[EW_TILE];
+    __shared__ uint32_t s_n;
+    __shared__ int      s_best[8];
+    __shared__ uint32_t s_heads[8];
     const uint32_t b = blockIdx.y;
     if (skip[b]) return;
     const uint32_t p     = period[b];
@@ -460,34 +470,44 @@ __global__ void __launch_bounds__(EW_THREADS)
     const uint32_t hm   = h % p;
     uint32_t       heads = 0;
     int            best  = -1;  // last head that lands in this tile
-    __shared__ int      s_best[8];
-    __shared__ uint32_t s_heads[8];
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
     for (uint32_t j = tile0 + threadIdx.x; j < tend; j += EW_THREADS)
     {
-        const uint32_t me = sa[base + j];
-        uint32_t       pos = j;
-        bool           head = true;
-        if (!(fo[j] && (j + 1 == p || fo[j + 1])))
+        if (fo[j] && (j + 1 == p || fo[j + 1]))
         {
-            uint32_t s = j, e = j + 1;
-            while (!fo[s]) --s;            // slot 0 is always a head
-            while (e < p && !fo[e]) ++e;
-            uint32_t less = 0, tie_before = 0;
-            for (uint32_t m = s; m < e; ++m)
-            {
-                if (m == j) continue;
-                const int c = rot_cmp_window(T, p, me, sa[base + m], hm);
-                if (c > 0)
-                    ++less;
-                else if (c == 0 && m < j)
-                {
-                    ++less;
-                    ++tie_before;
-                }
-            }
-            pos  = s + less;
-            head = tie_before == 0;
+            sa_out[base + j]    = sa[base + j];
+            flags_new[base + j] = 1;
+            ++heads;
+            best = (int) j;  // j grows along the loop
         }
+        else
+            s_list[atomicAdd(&s_n, 1u)] = (uint16_t) (j - tile0);
+    }
+    __syncthreads();
+    const uint32_t nlist = s_n;
+    for (uint32_t x = threadIdx.x; x < nlist; x += EW_THREADS)
+    {
+        const uint32_t j  = tile0 + s_list[x];
+        const uint32_t me = sa[base + j];
+        uint32_t       s = j, e = j + 1;
+        while (!fo[s]) --s;  // slot 0 is always a head
+        while (e < p && !fo[e]) ++e;
+        uint32_t less = 0, tie_before = 0;
+        for (uint32_t m = s; m < e; ++m)
+        {
+            if (m == j) continue;
+            const int c = rot_cmp_window(T, p, me, sa[base + m], hm);
+            if (c > 0)
+                ++less;
+            else if (c == 0 && m < j)
+            {
+                ++less;
+                ++tie_before;
+            }
+        }
+        const uint32_t pos    = s + less;
+        const bool     head   = tie_before == 0;
         sa_out[base + pos]    = me;
         flags_new[base + pos] = head ? 1 : 0;
         if (head)
@@ -657,12 +677,27 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             bra_b200_log_error("bwt: divisor table overflow (%zu values, %u per block)", vals.size(), maxcnt);
             return false;
         }
-        BRA_CUDA_TRY(cudaMemcpyAsync(a.d_div_vals, vals.data(), vals.size() * 4, cudaMemcpyHostToDevice, st));
-        BRA_CUDA_TRY(cudaMemcpyAsync(a.d_div_off, off.data(), nblk * 4, cudaMemcpyHostToDevice, st));
-        BRA_CUDA_TRY(cudaMemcpyAsync(a.d_div_cnt, cnt.data(), nblk * 4, cudaMemcpyHostToDevice, st));
-        BRA_CUDA_TRY(cudaMemsetAsync(a.d_bad, 0, (size_t) nblk * a.bad_stride, st));
-        // the pageable-host staging vectors die at scope exit: the copies above must have landed
-        BRA_CUDA_TRY(cudaStreamSynchronize(st));
+        if (a.h_mail)
+        {
+            uint32_t* m = a.h_mail + 2;
+            memcpy(m, vals.data(), vals.size() * 4);
+            memcpy(m + a.div_cap, off.data(), (size_t) nblk * 4);
+            memcpy(m + a.div_cap + nblk, cnt.data(), (size_t) nblk * 4);
+            if (!mail_fetch(a.d_div_vals, m, (uint32_t) vals.size(), st) || !mail_fetch(a.d_div_off, m + a.div_cap, nblk, st) ||
+                !mail_fetch(a.d_div_cnt, m + a.div_cap + nblk, nblk, st))
+                return false;
+            BRA_CUDA_TRY(cudaMemsetAsync(a.d_bad, 0, (size_t) nblk * a.bad_stride, st));
+            // the mail words are rewritten by the next batch only, and the loop below synchronises long before that
+        }
+        else
+        {
+            BRA_CUDA_TRY(cudaMemcpyAsync(a.d_div_vals, vals.data(), vals.size() * 4, cudaMemcpyHostToDevice, st));
+            BRA_CUDA_TRY(cudaMemcpyAsync(a.d_div_off, off.data(), nblk * 4, cudaMemcpyHostToDevice, st));
+            BRA_CUDA_TRY(cudaMemcpyAsync(a.d_div_cnt, cnt.data(), nblk * 4, cudaMemcpyHostToDevice, st));
+            BRA_CUDA_TRY(cudaMemsetAsync(a.d_bad, 0, (size_t) nblk * a.bad_stride, st));
+            // the pageable-host staging vectors die at scope exit: the copies above must have landed
+            BRA_CUDA_TRY(cudaStreamSynchronize(st));
+        }
         BRA_LAUNCH(P_BWT_PERIOD, st, bwt_period_kernel<<<grid, 256, 0, st>>>(a.d_in, a.stride, a.d_len, a.d_div_vals, a.d_div_off, a.d_div_cnt, a.d_bad, a.bad_stride));
         BRA_LAUNCH(P_BWT_PERIOD, st, bwt_period_select_kernel<<<bra_div_up(nblk, 128), 128, 0, st>>>(a.d_len, a.d_div_vals, a.d_div_off, a.d_div_cnt, a.d_bad,
                                                                        a.bad_stride, a.d_period, nblk));
@@ -700,8 +735,18 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
                                                                           a.d_notdone, nblk));
         BRA_LAUNCH(P_BWT_GATHER, st, bwt_gather_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, vA, a.stride, a.d_len, a.d_period, a.d_done, a.d_out, a.d_primary));
         uint32_t stat[2] = {0, 0};
-        BRA_CUDA_TRY(cudaMemcpyAsync(stat, a.d_notdone, 8, cudaMemcpyDeviceToHost, st));
-        BRA_CUDA_TRY(cudaStreamSynchronize(st));
+        if (a.h_mail)
+        {
+            if (!mail_publish(a.h_mail, a.d_notdone, 2, st)) return false;
+            BRA_CUDA_TRY(cudaStreamSynchronize(st));
+            stat[0] = reinterpret_cast<volatile uint32_t*>(a.h_mail)[0];
+            stat[1] = reinterpret_cast<volatile uint32_t*>(a.h_mail)[1];
+        }
+        else
+        {
+            BRA_CUDA_TRY(cudaMemcpyAsync(stat, a.d_notdone, 8, cudaMemcpyDeviceToHost, st));
+            BRA_CUDA_TRY(cudaStreamSynchronize(st));
+        }
         if (stat[0] == 0) break;
         if (stat[1] != 0)
         {

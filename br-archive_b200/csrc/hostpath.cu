@@ -127,8 +127,25 @@ struct Pipe
         if (s_out) cudaStreamDestroy(s_out);
     }
 };
-// blocks per pipeline stage: a quarter of the context's batch keeps the kernels wide and hides three quarters of the copies
-inline uint32_t stage_blocks(uint32_t max_batch) { return max_batch >= 64 ? max_batch / 4 : max_batch; }
+// Largest pipeline stage: half of the context's batch.
+inline uint32_t stage_blocks(uint32_t max_batch) { return max_batch >= 64 ? max_batch / 2 : max_batch; }
+// Blocks per stage. Only the first input copy and the last output copy are not hidden behind kernels, while wide
+// stages run the kernels at their best rate -- so the stages grow geometrically from an eighth of the largest one.
+// Encoding wants the short stage first (its input is the big copy), decoding wants it last (its output is).
+inline std::vector<uint32_t> stage_plan(uint64_t nblk, uint32_t hb, bool short_first)
+{
+    std::vector<uint32_t> plan;
+    uint64_t              left = nblk;
+    for (uint32_t s = std::max(1u, hb / 8); left > 0;)
+    {
+        const uint32_t take = (uint32_t) std::min<uint64_t>(left, s);
+        plan.push_back(take);
+        left -= take;
+        s = std::min(hb, s * 2);
+    }
+    if (!short_first) std::reverse(plan.begin(), plan.end());
+    return plan;
+}
 }  // namespace
 
 // Three streams: input copies run one stage ahead of the kernels, output copies one stage behind
@@ -147,7 +164,10 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
     const uint32_t HB = stage_blocks(bra_b200_max_batch(c));
     const uint64_t PS = bra_b200_payload_stride(c);
     const uint64_t nblk_total = (total + S - 1) / S;
-    const uint64_t nstage     = (nblk_total + HB - 1) / HB;
+    const std::vector<uint32_t> plan = stage_plan(nblk_total, HB, /*short_first=*/true);
+    const uint64_t        nstage = plan.size();
+    std::vector<uint64_t> first(nstage + 1, 0);  // first block of every stage
+    for (uint64_t i = 0; i < nstage; ++i) first[i + 1] = first[i] + plan[i];
     cudaStream_t   st = ctx_stream(c);
     *out_size         = 0;
     Pipe P;
@@ -168,10 +188,11 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
     uint32_t* d_hcrc   = d_crc + HB;
 
     const bra_gf_pow_t*   pw = crc_host_pow();
+    uint32_t*             mail = ctx_mail_host(c);
     std::vector<uint32_t> h_crc(2 * (size_t) HB);
     uint32_t              crc = crc_chain ? *crc_chain : 0;
     uint64_t              produced = 0;
-    auto stage_bytes = [&](uint64_t i) { return std::min<uint64_t>((uint64_t) HB * S, total - i * HB * S); };
+    auto stage_bytes = [&](uint64_t i) { return std::min<uint64_t>((uint64_t) plan[i] * S, total - first[i] * S); };
 
     if (cudaMemcpyAsync(d_in[0], in, stage_bytes(0), cudaMemcpyHostToDevice, P.s_in) != cudaSuccess) return 4;
     cudaEventRecord(P.ev_in[0], P.s_in);
@@ -185,7 +206,7 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
         {
             // prefetch the next stage's input; its slot was last read by the kernels of stage i-1
             if (i >= 1) cudaStreamWaitEvent(P.s_in, P.ev_comp[slot ^ 1], 0);
-            if (cudaMemcpyAsync(d_in[slot ^ 1], in + (i + 1) * HB * S, stage_bytes(i + 1), cudaMemcpyHostToDevice, P.s_in) != cudaSuccess) return 4;
+            if (cudaMemcpyAsync(d_in[slot ^ 1], in + first[i + 1] * S, stage_bytes(i + 1), cudaMemcpyHostToDevice, P.s_in) != cudaSuccess) return 4;
             cudaEventRecord(P.ev_in[slot ^ 1], P.s_in);
         }
         cudaStreamWaitEvent(st, P.ev_in[slot], 0);
@@ -195,12 +216,14 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
         BRA_LAUNCH(P_GLUE, st, stream_offsets_kernel<<<1, 1024, 0, st>>>(d_hdr, nb, d_off));
         const uint32_t gx = bra_div_up(267 + PS, 4096);
         BRA_LAUNCH(P_GLUE, st, stream_gather_kernel<<<dim3(gx, nb), 256, 0, st>>>(d_hdr, d_pay, PS, d_off, d_str[slot]));
-        uint64_t str_size = 0;
-        if (cudaMemcpyAsync(&str_size, d_off + nb, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
-        if (cudaMemcpyAsync(h_crc.data(), d_crc, (size_t) nb * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
-        if (cudaMemcpyAsync(h_crc.data() + HB, d_hcrc, (size_t) nb * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+        // stream size and the per-chunk CRCs come back through the mail words: a small cudaMemcpy would wait on the
+        // device-to-host copy engine behind the previous stage's stream
+        if (!mail_publish(mail, reinterpret_cast<const uint32_t*>(d_off + nb), 2, st) || !mail_publish(mail + 16, d_crc, 2 * HB, st)) return 5;
         cudaEventRecord(P.ev_comp[slot], st);
         if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
+        uint64_t str_size = 0;
+        memcpy(&str_size, mail, 8);
+        memcpy(h_crc.data(), mail + 16, (size_t) 2 * HB * 4);
         if (produced + str_size > out_cap)
         {
             bra_b200_log_error("bra_b200_encode_host: output buffer too small");
@@ -268,37 +291,48 @@ static int decode_host_impl(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_si
     std::vector<Stage>    stages;
     std::vector<uint64_t> offs;  // per stage: nb+1 offsets relative to the stage start, concatenated
     {
-        uint64_t p = 0;
+        struct Chunk
+        {
+            uint64_t pos;
+            uint32_t r, c;
+        };
+        std::vector<Chunk> chunks;
+        uint64_t           p = 0;
         while (p < in_size)
         {
-            Stage sg{p, p, 0, 0, 0};
-            while (sg.nb < HB && p < in_size)
+            if (in_size - p < 267)
             {
-                if (in_size - p < 267)
-                {
-                    bra_b200_log_error("bra_b200_decode_host: truncated chunk header at offset %llu", (unsigned long long) p);
-                    return 7;
-                }
-                const uint8_t* h = in + p + 3 + 256;
-                const uint32_t r = (uint32_t) h[0] | ((uint32_t) h[1] << 8) | ((uint32_t) h[2] << 16) | ((uint32_t) h[3] << 24);
-                const uint32_t cc = (uint32_t) h[4] | ((uint32_t) h[5] << 8) | ((uint32_t) h[6] << 16) | ((uint32_t) h[7] << 24);
-                if (cc == 0 || r == 0 || cc > PS - 32 || in_size - p - 267 < cc)
-                {
-                    bra_b200_log_error("bra_b200_decode_host: chunk header not valid at offset %llu", (unsigned long long) p);
-                    return 7;
-                }
-                offs.push_back(p - sg.pos);
-                sg.max_r = std::max(sg.max_r, r);
-                sg.max_c = std::max(sg.max_c, cc);
-                p += 267 + cc;
-                ++sg.nb;
+                bra_b200_log_error("bra_b200_decode_host: truncated chunk header at offset %llu", (unsigned long long) p);
+                return 7;
             }
-            offs.push_back(p - sg.pos);
-            sg.end = p;
+            const uint8_t* h = in + p + 3 + 256;
+            const uint32_t r = (uint32_t) h[0] | ((uint32_t) h[1] << 8) | ((uint32_t) h[2] << 16) | ((uint32_t) h[3] << 24);
+            const uint32_t cc = (uint32_t) h[4] | ((uint32_t) h[5] << 8) | ((uint32_t) h[6] << 16) | ((uint32_t) h[7] << 24);
+            if (cc == 0 || r == 0 || cc > PS - 32 || in_size - p - 267 < cc)
+            {
+                bra_b200_log_error("bra_b200_decode_host: chunk header not valid at offset %llu", (unsigned long long) p);
+                return 7;
+            }
+            chunks.push_back({p, r, cc});
+            p += 267 + cc;
+        }
+        size_t k = 0;
+        for (const uint32_t nb : stage_plan(chunks.size(), HB, /*short_first=*/false))
+        {
+            Stage sg{chunks[k].pos, 0, nb, 0, 0};
+            for (uint32_t b = 0; b < nb; ++b, ++k)
+            {
+                offs.push_back(chunks[k].pos - sg.pos);
+                sg.max_r = std::max(sg.max_r, chunks[k].r);
+                sg.max_c = std::max(sg.max_c, chunks[k].c);
+            }
+            sg.end = k < chunks.size() ? chunks[k].pos : in_size;
+            offs.push_back(sg.end - sg.pos);
             stages.push_back(sg);
         }
     }
     const bra_gf_pow_t*   pw = crc_host_pow();
+    uint32_t*             mail = ctx_mail_host(c);
     std::vector<uint64_t> h_ooff(HB + 1);
     std::vector<uint32_t> h_misc(4 * (size_t) HB);
     uint32_t              crc = crc_chain ? *crc_chain : 0;
@@ -329,8 +363,10 @@ static int decode_host_impl(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_si
         BRA_LAUNCH(P_GLUE, st, stream_scatter_kernel<<<dim3(gx, sg.nb), 256, 0, st>>>(d_str[slot], d_off[slot], d_hdr, d_pay, PS));
         if (!decode_batch(c, d_hdr, d_pay, sg.nb, sg.max_r, sg.max_c, d_out[slot], d_len, d_crc, d_stat, st, sizes_only)) return 5;
         if (!crc_headers(d_hdr, 268, sg.nb, d_hcrc, st)) return 5;
-        if (cudaMemcpyAsync(h_misc.data(), d_len, (size_t) 4 * HB * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return 4;
+        // lengths, CRCs and status come back through the mail words (see encode)
+        if (!mail_publish(mail, d_len, 4 * HB, st)) return 5;
         if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
+        memcpy(h_misc.data(), mail, (size_t) 4 * HB * 4);
         if (sizes_only)
         {
             for (uint32_t b = 0; b < sg.nb; ++b)

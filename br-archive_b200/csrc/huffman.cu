@@ -641,6 +641,21 @@ __global__ void huf_dec_trailing_kernel(const uint8_t* __restrict__ pay, uint64_
         }
 }
 
+// sweep status back to the host (through the mail word when there is one, see BwtFwdArgs::h_mail)
+static bool read_changed(const HufDecArgs& a, cudaStream_t st, uint32_t* changed)
+{
+    if (a.h_mail)
+    {
+        if (!mail_publish(a.h_mail, a.d_changed, 1, st)) return false;
+        BRA_CUDA_TRY(cudaStreamSynchronize(st));
+        *changed = *reinterpret_cast<volatile uint32_t*>(a.h_mail);
+        return true;
+    }
+    BRA_CUDA_TRY(cudaMemcpyAsync(changed, a.d_changed, 4, cudaMemcpyDeviceToHost, st));
+    BRA_CUDA_TRY(cudaStreamSynchronize(st));
+    return true;
+}
+
 bool huf_decode_batch(const HufDecArgs& a, cudaStream_t st)
 {
     if (a.nblk == 0 || a.max_c == 0) return true;
@@ -659,8 +674,7 @@ bool huf_decode_batch(const HufDecArgs& a, cudaStream_t st)
                                                              a.d_sub_count, a.d_seq_entry, a.d_seq_exit, a.d_seq_count, a.d_changed));
         sweeps += 2;
         uint32_t changed = 0;
-        BRA_CUDA_TRY(cudaMemcpyAsync(&changed, a.d_changed, 4, cudaMemcpyDeviceToHost, st));
-        BRA_CUDA_TRY(cudaStreamSynchronize(st));
+        if (!read_changed(a, st, &changed)) return false;
         // the first pair of sweeps always reports changes (every CTA publishes its first exit)
         if (changed == 0 || sweeps > 2 * seqs + 4) break;
         if (sweeps == 2)
@@ -670,8 +684,7 @@ bool huf_decode_batch(const HufDecArgs& a, cudaStream_t st)
             BRA_LAUNCH(P_HUF_DEC_SYNC, st, huf_dec_sync_kernel<<<grid, HD_THREADS, 0, st>>>(a.d_pay, a.pay_stride, a.d_clen, a.d_tabs, a.d_err, seqs, a.d_sub_start,
                                                              a.d_sub_count, a.d_seq_entry, a.d_seq_exit, a.d_seq_count, a.d_changed));
             ++sweeps;
-            BRA_CUDA_TRY(cudaMemcpyAsync(&changed, a.d_changed, 4, cudaMemcpyDeviceToHost, st));
-            BRA_CUDA_TRY(cudaStreamSynchronize(st));
+            if (!read_changed(a, st, &changed)) return false;
             if (changed == 0) break;
         }
     }

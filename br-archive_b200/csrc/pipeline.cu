@@ -145,9 +145,37 @@ struct bra_b200_ctx
     uint64_t d_io_bytes = 0;
     uint32_t last_rounds = 0, last_sweeps = 0;
     uint64_t last_launches = 0;
+    // pinned, device-visible host words for the small transfers of the control loops (mail_fetch / mail_publish):
+    // [bwt: 2 + BRA_DIV_CAP + 2*max_batch][huffman: 16][block lengths: max_batch][host path: 8*max_batch + 16]
+    uint32_t* h_mail = nullptr;
 };
 
+static inline uint32_t* mail_bwt(bra_b200_ctx* c) { return c->h_mail; }
+static inline uint32_t* mail_huffman(bra_b200_ctx* c) { return c->h_mail + 2 + BRA_DIV_CAP + 2 * (size_t) c->max_batch; }
+static inline uint32_t* mail_lengths(bra_b200_ctx* c) { return mail_huffman(c) + 16; }
+
 // ---- small glue kernels -------------------------------------------------------------------------
+__global__ void mail_copy_kernel(uint32_t* __restrict__ dst, const uint32_t* __restrict__ src, uint32_t words)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < words) dst[i] = src[i];
+}
+namespace bra {
+bool mail_fetch(uint32_t* d_dst, const uint32_t* h_src, uint32_t words, cudaStream_t st)
+{
+    if (words == 0) return true;
+    BRA_LAUNCH(P_GLUE, st, mail_copy_kernel<<<bra_div_up(words, 256), 256, 0, st>>>(d_dst, h_src, words));
+    BRA_CUDA_TRY(cudaGetLastError());
+    return true;
+}
+bool mail_publish(uint32_t* h_dst, const uint32_t* d_src, uint32_t words, cudaStream_t st)
+{
+    if (words == 0) return true;
+    BRA_LAUNCH(P_GLUE, st, mail_copy_kernel<<<bra_div_up(words, 256), 256, 0, st>>>(h_dst, d_src, words));
+    BRA_CUDA_TRY(cudaGetLastError());
+    return true;
+}
+}  // namespace bra
 __global__ void set_primary_kernel(uint8_t* __restrict__ hdr, const uint32_t* __restrict__ primary, uint32_t nblk)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,8 +275,11 @@ extern "C" bra_b200_ctx_t* bra_b200_ctx_create(int device, uint32_t block_size, 
         return nullptr;
     }
     c->arena.cap = need;
-    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+    const size_t mail_words = (2 + BRA_DIV_CAP + 2 * (size_t) max_batch) + 16 + max_batch + (8 * (size_t) max_batch + 16);
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc(reinterpret_cast<void**>(&c->h_mail), mail_words * 4, cudaHostAllocPortable | cudaHostAllocMapped) != cudaSuccess)
     {
+        if (c->own_stream) cudaStreamDestroy(c->own_stream);
         cudaFree(c->arena.base);
         delete c;
         return nullptr;
@@ -263,6 +294,7 @@ extern "C" void bra_b200_ctx_destroy(bra_b200_ctx_t* c)
     if (c->arena.base) cudaFree(c->arena.base);
     if (c->d_io) cudaFree(c->d_io);
     if (c->h_stage) cudaFreeHost(c->h_stage);
+    if (c->h_mail) cudaFreeHost(c->h_mail);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -293,8 +325,9 @@ bool encode_batch(bra_b200_ctx* c, const uint8_t* d_in, uint32_t nb, uint32_t la
 
     std::vector<uint32_t> h_len(nb, S);
     h_len[nb - 1] = last_len;
-    BRA_CUDA_TRY(cudaMemcpyAsync(w.len, h_len.data(), nb * 4, cudaMemcpyHostToDevice, st));
-    BRA_CUDA_TRY(cudaStreamSynchronize(st));  // h_len is pageable stack-owned memory
+    uint32_t* mail_len = mail_lengths(c);
+    memcpy(mail_len, h_len.data(), (size_t) nb * 4);
+    if (!mail_fetch(w.len, mail_len, nb, st)) return false;  // rewritten by the next batch only, after many stream syncs
 
     if (!crc_blocks(d_in, S, w.len, 0, S, nb, nullptr, d_crc, st)) return false;
 
@@ -308,6 +341,7 @@ bool encode_batch(bra_b200_ctx* c, const uint8_t* d_in, uint32_t nb, uint32_t la
     ba.d_bad = w.bad; ba.bad_stride = BRA_BAD_STRIDE;
     uint32_t rounds = 0;
     ba.h_rounds = &rounds;
+    ba.h_mail   = mail_bwt(c);
     if (!bwt_forward_batch(ba, st)) return false;
     c->last_rounds = std::max(c->last_rounds, rounds);
 
@@ -353,6 +387,7 @@ bool decode_batch(bra_b200_ctx* c, const uint8_t* d_hdr, const uint8_t* d_payloa
     ha.d_seq_count = w.seq_count; ha.d_end_bit = w.end_bit; ha.d_changed = w.changed;
     uint32_t sweeps = 0;
     ha.h_sweeps = &sweeps;
+    ha.h_mail   = mail_huffman(c);
     if (!huf_decode_batch(ha, st)) return false;
     c->last_sweeps = std::max(c->last_sweeps, sweeps);
     BRA_LAUNCH(P_GLUE, st, zero_len_on_err_kernel<<<bra_div_up(nb, 128), 128, 0, st>>>(w.rlen, w.err, nb));
@@ -460,5 +495,6 @@ uint8_t* ctx_io_buffer(bra_b200_ctx* c, uint64_t bytes)
     return c->d_io;
 }
 cudaStream_t ctx_stream(bra_b200_ctx* c) { return c->own_stream; }
+uint32_t*    ctx_mail_host(bra_b200_ctx* c) { return mail_lengths(c) + c->max_batch; }  // 8*max_batch + 16 words for the host path
 int          ctx_device(const bra_b200_ctx* c) { return c->device; }
 }  // namespace bra

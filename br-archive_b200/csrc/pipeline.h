@@ -15,5 +15,6 @@ bool decode_batch(bra_b200_ctx* c, const uint8_t* d_hdr, const uint8_t* d_payloa
 // device staging buffer of the context for the host path (grown on demand)
 uint8_t* ctx_io_buffer(bra_b200_ctx* c, uint64_t bytes);
 cudaStream_t ctx_stream(bra_b200_ctx* c);
+uint32_t* ctx_mail_host(bra_b200_ctx* c);  // pinned, device-visible words for the host path (8*max_batch + 16)
 int ctx_device(const bra_b200_ctx* c);
 }  // namespace bra
