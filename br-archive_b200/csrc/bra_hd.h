@@ -259,3 +259,36 @@ BRA_HD uint32_t bra_huf_decode_one(const bra_huf_dec_t* d, uint32_t w, uint8_t* 
     }
     return 0;
 }
+
+// ---- host-path pipeline: blocks per stage ------------------------------------------------------------------------
+// Every stage costs a few milliseconds of latency-bound kernels whatever its size; the input copy of a stage hides
+// behind the kernels of the stage before it and its output copy behind those of the stage after it, so only the
+// first input copy and the last output copy are exposed. Hence a short head (a tenth of the job, long enough for
+// its kernels to cover the next input copy), stages as wide as the context allows (`hb` blocks), and a tail that
+// shrinks (a quarter, then a sixteenth) so that each output copy fits behind the kernels that follow. The same
+// plan serves both directions and any compression ratio. Writes at most nblk / hb + 4 entries; returns the count.
+static inline uint32_t bra_stage_plan(uint64_t nblk, uint32_t hb, uint32_t* plan)
+{
+    uint32_t n = 0;
+    if (nblk == 0 || hb == 0) return 0;
+    if (nblk < 128 && nblk <= hb)
+    {
+        if (nblk > 1) plan[n++] = (uint32_t) (nblk / 2);
+        plan[n++] = (uint32_t) (nblk - nblk / 2);
+        return n;
+    }
+    const uint64_t tail1 = nblk / 4 < hb ? nblk / 4 : hb, tail2 = nblk / 16 < hb ? nblk / 16 : hb;
+    uint64_t       head  = nblk / 10 > 16 ? nblk / 10 : 16;
+    if (head > hb) head = hb;
+    if (head > nblk - tail1 - tail2) head = nblk - tail1 - tail2;
+    if (head) plan[n++] = (uint32_t) head;
+    for (uint64_t left = nblk - head - tail1 - tail2; left > 0;)
+    {
+        const uint64_t take = left < hb ? left : hb;
+        plan[n++] = (uint32_t) take;
+        left -= take;
+    }
+    if (tail1) plan[n++] = (uint32_t) tail1;
+    if (tail2) plan[n++] = (uint32_t) tail2;
+    return n;
+}

@@ -61,4 +61,7 @@ int hl_huf_decode(const uint8_t* lengths, const uint8_t* data, uint32_t nbytes, 
     return 0;
 }
 
+// host-path pipeline plan (bra_stage_plan); `plan` must hold nblk / hb + 4 entries
+uint32_t hl_stage_plan(uint64_t nblk, uint32_t hb, uint32_t* plan) { return bra_stage_plan(nblk, hb, plan); }
+
 }  // extern "C"

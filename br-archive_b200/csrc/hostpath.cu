@@ -9,6 +9,7 @@
 //         payload size), uploaded as is, scattered on the device into the batched layout, decoded,
 //         and the plain bytes come back with one D2H copy per batch.
 #include "bra_common.cuh"
+#include "bra_hd.h"
 #include "bra_kernels.h"
 #include "pipeline.h"
 
@@ -17,6 +18,31 @@
 #include <vector>
 
 using namespace bra;
+
+// BRA_B200_TRACE=1: per-stage host timestamps of the host-buffer path on stderr (diagnostics only)
+#include <chrono>
+#include <stdio.h>
+#include <stdlib.h>
+static bool trace_on()
+{
+    static const bool on = getenv("BRA_B200_TRACE") != nullptr;
+    return on;
+}
+static double trace_ms()
+{
+    using namespace std::chrono;
+    static const steady_clock::time_point t0 = steady_clock::now();
+    return duration<double, std::milli>(steady_clock::now() - t0).count();
+}
+#define BRA_TRACE(...)                          \
+    do {                                        \
+        if (trace_on())                         \
+        {                                       \
+            fprintf(stderr, "[bra trace %9.3f] ", trace_ms()); \
+            fprintf(stderr, __VA_ARGS__);       \
+            fputc('\n', stderr);                \
+        }                                       \
+    } while (0)
 
 namespace {
 
@@ -127,23 +153,13 @@ struct Pipe
         if (s_out) cudaStreamDestroy(s_out);
     }
 };
-// Largest pipeline stage: half of the context's batch.
-inline uint32_t stage_blocks(uint32_t max_batch) { return max_batch >= 64 ? max_batch / 2 : max_batch; }
-// Blocks per stage. Only the first input copy and the last output copy are not hidden behind kernels, while wide
-// stages run the kernels at their best rate -- so the stages grow geometrically from an eighth of the largest one.
-// Encoding wants the short stage first (its input is the big copy), decoding wants it last (its output is).
-inline std::vector<uint32_t> stage_plan(uint64_t nblk, uint32_t hb, bool short_first)
+// Largest pipeline stage: the context's whole batch.
+inline uint32_t stage_blocks(uint32_t max_batch) { return max_batch; }
+// blocks per stage: bra_stage_plan (bra_hd.h)
+inline std::vector<uint32_t> stage_plan(uint64_t nblk, uint32_t hb)
 {
-    std::vector<uint32_t> plan;
-    uint64_t              left = nblk;
-    for (uint32_t s = std::max(1u, hb / 8); left > 0;)
-    {
-        const uint32_t take = (uint32_t) std::min<uint64_t>(left, s);
-        plan.push_back(take);
-        left -= take;
-        s = std::min(hb, s * 2);
-    }
-    if (!short_first) std::reverse(plan.begin(), plan.end());
+    std::vector<uint32_t> plan(nblk / std::max(1u, hb) + 4);
+    plan.resize(bra_stage_plan(nblk, hb, plan.data()));
     return plan;
 }
 }  // namespace
@@ -164,7 +180,7 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
     const uint32_t HB = stage_blocks(bra_b200_max_batch(c));
     const uint64_t PS = bra_b200_payload_stride(c);
     const uint64_t nblk_total = (total + S - 1) / S;
-    const std::vector<uint32_t> plan = stage_plan(nblk_total, HB, /*short_first=*/true);
+    const std::vector<uint32_t> plan = stage_plan(nblk_total, HB);
     const uint64_t        nstage = plan.size();
     std::vector<uint64_t> first(nstage + 1, 0);  // first block of every stage
     for (uint64_t i = 0; i < nstage; ++i) first[i + 1] = first[i] + plan[i];
@@ -211,6 +227,7 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
         }
         cudaStreamWaitEvent(st, P.ev_in[slot], 0);
         if (i >= 2) cudaStreamWaitEvent(st, P.ev_out[slot], 0);  // the stream slot is free once stage i-2 has left the device
+        BRA_TRACE("encode stage %llu: %u blocks, kernels enqueued from here", (unsigned long long) i, nb);
         if (!encode_batch(c, d_in[slot], nb, last, d_hdr, d_pay, d_crc, st)) return 5;
         if (!crc_headers(d_hdr, 268, nb, d_hcrc, st)) return 5;
         BRA_LAUNCH(P_GLUE, st, stream_offsets_kernel<<<1, 1024, 0, st>>>(d_hdr, nb, d_off));
@@ -223,6 +240,7 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
         if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
         uint64_t str_size = 0;
         memcpy(&str_size, mail, 8);
+        BRA_TRACE("encode stage %llu: kernels done, %llu stream bytes", (unsigned long long) i, (unsigned long long) str_size);
         memcpy(h_crc.data(), mail + 16, (size_t) 2 * HB * 4);
         if (produced + str_size > out_cap)
         {
@@ -242,6 +260,7 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
         produced += str_size;
     }
     if (cudaStreamSynchronize(P.s_out) != cudaSuccess || cudaStreamSynchronize(P.s_in) != cudaSuccess) return 4;
+    BRA_TRACE("encode: last output copy done");
     *out_size = produced;
     if (crc_chain) *crc_chain = crc;
     return 0;
@@ -317,7 +336,7 @@ static int decode_host_impl(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_si
             p += 267 + cc;
         }
         size_t k = 0;
-        for (const uint32_t nb : stage_plan(chunks.size(), HB, /*short_first=*/false))
+        for (const uint32_t nb : stage_plan(chunks.size(), HB))
         {
             Stage sg{chunks[k].pos, 0, nb, 0, 0};
             for (uint32_t b = 0; b < nb; ++b, ++k)
@@ -360,6 +379,7 @@ static int decode_host_impl(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_si
         cudaStreamWaitEvent(st, P.ev_in[slot], 0);
         if (i >= 2) cudaStreamWaitEvent(st, P.ev_out[slot], 0);  // output slot free once stage i-2 has been copied out
         const uint32_t gx = bra_div_up(267 + (uint64_t) sg.max_c, 4096);
+        BRA_TRACE("decode stage %zu: %u chunks, kernels enqueued from here", i, sg.nb);
         BRA_LAUNCH(P_GLUE, st, stream_scatter_kernel<<<dim3(gx, sg.nb), 256, 0, st>>>(d_str[slot], d_off[slot], d_hdr, d_pay, PS));
         if (!decode_batch(c, d_hdr, d_pay, sg.nb, sg.max_r, sg.max_c, d_out[slot], d_len, d_crc, d_stat, st, sizes_only)) return 5;
         if (!crc_headers(d_hdr, 268, sg.nb, d_hcrc, st)) return 5;
@@ -367,6 +387,7 @@ static int decode_host_impl(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_si
         if (!mail_publish(mail, d_len, 4 * HB, st)) return 5;
         if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
         memcpy(h_misc.data(), mail, (size_t) 4 * HB * 4);
+        BRA_TRACE("decode stage %zu: kernels done", i);
         if (sizes_only)
         {
             for (uint32_t b = 0; b < sg.nb; ++b)
@@ -425,6 +446,7 @@ static int decode_host_impl(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_si
         produced += o;
     }
     if (cudaStreamSynchronize(P.s_out) != cudaSuccess || cudaStreamSynchronize(P.s_in) != cudaSuccess) return 4;
+    BRA_TRACE("decode: last output copy done");
     *out_size = produced;
     if (crc_chain) *crc_chain = crc;
     return 0;

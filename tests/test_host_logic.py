@@ -107,3 +107,19 @@ def test_crc_fold(hl, oracle):
     # long zero runs: combine with huge lengths must agree with the oracle's square-and-multiply
     for ln in (1 << 20, (1 << 32) - 1, 123456789):
         assert hl.hl_crc_combine(0x12345678, 0x9ABCDEF0, ln) == oracle.crc32c_combine(0x12345678, 0x9ABCDEF0, ln)
+
+
+def test_stage_plan_covers_every_block(hl):
+    """bra_stage_plan (host-path pipeline): stages are non-empty, never wider than the context's batch, and add up to the job."""
+    hl.hl_stage_plan.restype = C.c_uint32
+    hl.hl_stage_plan.argtypes = [C.c_uint64, C.c_uint32, u32p]
+    for hb in (1, 2, 3, 4, 8, 16, 64, 256, 1024, 32768):
+        for n in list(range(1, 700)) + [1023, 1024, 1025, 4096, 5000, 65536, 100003]:
+            plan = np.zeros(n // hb + 4, dtype=np.uint32)
+            k = hl.hl_stage_plan(n, hb, plan.ctypes.data_as(u32p))
+            assert 1 <= k <= len(plan)
+            p = plan[:k]
+            assert p.min() >= 1 and p.max() <= hb and int(p.sum()) == n, (n, hb, p.tolist())
+    plan = np.zeros(8, dtype=np.uint32)
+    k = hl.hl_stage_plan(1024, 1024, plan.ctypes.data_as(u32p))
+    assert plan[:k].tolist() == [102, 602, 256, 64]  # short head, wide middle, shrinking tail
