@@ -241,23 +241,38 @@ __global__ void __launch_bounds__(32)
     const uint32_t nseg = (n + MTF_SEG - 1) / MTF_SEG;
     for (int i = lane; i < 256; i += 32) cur[i] = (uint8_t) i;
     __syncwarp();
+    // the walk is a chain of dependent steps: the next segment's summary is fetched while the current one is applied
+    const uint2* sm2   = reinterpret_cast<const uint2*>(summ + (uint64_t) b * segs * 256);
+    uint2        nextv = nseg > 1 ? sm2[lane] : make_uint2(0, 0);
+    uint32_t     nextk = (ENCODE && nseg > 1) ? scnt[(uint64_t) b * segs] : 0u;
     for (uint32_t s = 0; s < nseg; ++s)
     {
-        uint8_t*       st = state + ((uint64_t) b * segs + s) * 256;
-        const uint8_t* sm = summ + ((uint64_t) b * segs + s) * 256;
+        uint8_t* st = state + ((uint64_t) b * segs + s) * 256;
         reinterpret_cast<uint2*>(st)[lane] = reinterpret_cast<const uint2*>(cur)[lane];
         if (s + 1 == nseg) break;
+        const uint2    v = nextv;  // summary of segment s: bytes 8*lane .. 8*lane+7
+        const uint32_t k = nextk;
+        if (s + 2 < nseg)
+        {
+            nextv = sm2[(uint64_t) (s + 1) * 32 + lane];
+            if (ENCODE) nextk = scnt[(uint64_t) b * segs + s + 1];
+        }
+        const uint32_t vw[2] = {v.x, v.y};
         if (ENCODE)
         {
             // new list = segment's recency list, then the old list minus those symbols (order kept)
-            const uint32_t k = scnt[(uint64_t) b * segs + s];
             for (int i = lane; i < 256; i += 32) member[i] = 0;
             __syncwarp();
-            for (uint32_t i = lane; i < k; i += 32)
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
             {
-                const uint8_t sy = sm[i];
-                nxt[i]           = sy;
-                member[sy]       = 1;
+                const uint32_t i = lane * 8 + j;
+                if (i < k)
+                {
+                    const uint8_t sy = (uint8_t) (vw[j >> 2] >> ((j & 3) * 8));
+                    nxt[i]           = sy;
+                    member[sy]       = 1;
+                }
             }
             __syncwarp();
             uint32_t outp = k;
@@ -273,10 +288,11 @@ __global__ void __launch_bounds__(32)
         else
         {
             // positions are permuted: new[j] = old[perm[j]]
-            for (int i = lane; i < 256; i += 32) nxt[i] = cur[sm[i]];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) nxt[lane * 8 + j] = cur[(vw[j >> 2] >> ((j & 3) * 8)) & 0xFFu];
         }
         __syncwarp();
-        for (int i = lane; i < 256; i += 32) cur[i] = nxt[i];
+        reinterpret_cast<uint2*>(cur)[lane] = reinterpret_cast<const uint2*>(nxt)[lane];
         __syncwarp();
     }
 }
