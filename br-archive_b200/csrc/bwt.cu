@@ -259,6 +259,9 @@ __global__ void __launch_bounds__(EW_THREADS)
 
 // Pass B: rank[SA[j]] = index of the head of j's group, in place. Slots that were singleton groups
 // before this round (flags_old) keep their rank and are not touched.
+// WHAT 0: ranks and group statistics; 1: statistics only (the ranks are written later, and only if the
+// block goes on doubling -- a block the finisher completes never reads them); 2: ranks only.
+template <int WHAT>
 __global__ void __launch_bounds__(EW_THREADS)
     bwt_ranks_kernel(const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ flags_old, uint64_t stride,
                      const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, const int* __restrict__ tile_last, uint32_t tiles,
@@ -317,8 +320,9 @@ __global__ void __launch_bounds__(EW_THREADS)
             run = (int) j;
         }
         const bool settled = ((oldmask >> i) & 3u) == 3u;  // was a singleton group already: rank unchanged
-        if (!settled) rank_out[base + sa[base + j0 + i]] = (uint32_t) run;
+        if (WHAT != 1 && !settled) rank_out[base + sa[base + j0 + i]] = (uint32_t) run;
     }
+    if (WHAT == 2) return;
     if (m && j0 + m == p)  // the last group of the block ends at p
     {
         const uint32_t g = p - (uint32_t) run;
@@ -384,6 +388,12 @@ __global__ void bwt_reset_stats_kernel(const uint8_t* __restrict__ skip, uint32_
     ngroups[b]  = 0;
     maxgroup[b] = 0;
     sumsq[b]    = 0;
+}
+
+__global__ void bwt_reset_tile_last_kernel(const uint8_t* __restrict__ skip, int* __restrict__ tile_last, uint32_t tiles)
+{
+    const uint32_t b = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (!skip[b] && t < tiles) tile_last[(uint64_t) b * tiles + t] = -1;
 }
 
 // Finisher: when the remaining groups are small, order each of them by comparing the rotations
@@ -722,8 +732,11 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_done, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
     BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<0><<<grid, EW_THREADS, 0, st>>>(kA, vA, nullptr, 0, a.stride, a.d_period, a.d_done, nullptr, fcur, a.d_tile_last, tiles,
                                                       a.d_ngroups));
-    BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fcur, nullptr, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
-                                                                          a.d_maxgroup, a.d_sumsq, a.d_ngroups));
+    BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fcur, nullptr, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
+                                                                             a.d_maxgroup, a.d_sumsq, a.d_ngroups));
+    // the ranks themselves are written when (and for the blocks that) a doubling round follows
+    bool           ranks_pending = true;
+    const uint8_t* ranks_old     = nullptr;
 
     uint32_t h = 4, rounds = 0, finishes = 0;
     uint32_t key_bits = 1;
@@ -752,12 +765,17 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         {
             // finisher pass over the selected blocks (everything else keeps its state)
             BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_finskip, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
-            BRA_CUDA_TRY(cudaMemsetAsync(a.d_tile_last, 0xFF, (size_t) nblk * tiles * sizeof(int), st));
+            // (only the selected blocks: the others still need their tile carries for the pending rank pass)
+            BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_tile_last_kernel<<<dim3(bra_div_up(tiles, 256), nblk), 256, 0, st>>>(a.d_finskip, a.d_tile_last, tiles));
             BRA_LAUNCH(P_BWT_FINISH, st, bwt_finish_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, a.d_finskip, h, vA, fcur, vB, fnext,
                                                                                      a.d_tile_last, tiles, a.d_ngroups));
-            BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vB, fnext, fcur, a.stride, a.d_period, a.d_finskip, a.d_tile_last, tiles, rk,
+            BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vB, fnext, fcur, a.stride, a.d_period, a.d_finskip, a.d_tile_last, tiles, rk,
                                                                                   a.d_maxgroup, a.d_sumsq, a.d_ngroups));
             BRA_LAUNCH(P_BWT_FINISH, st, bwt_copyback_kernel<<<grid, EW_THREADS, 0, st>>>(a.stride, a.d_period, a.d_finskip, vB, vA, fnext, fcur));
+            // A block the finisher could not complete (rotations equal beyond its depth) goes on doubling: it needs every
+            // rank written, its slots were reordered. The pending rank pass therefore stops trusting the older flags.
+            ranks_pending = true;
+            ranks_old     = nullptr;
             ++finishes;
             continue;
         }
@@ -765,6 +783,12 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         {
             bra_b200_log_error("bwt: prefix doubling did not converge (h=%u, max_n=%u, %u blocks left)", h, max_n, stat[0]);
             return false;
+        }
+        if (ranks_pending)
+        {
+            BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<2><<<grid, EW_THREADS, 0, st>>>(vA, fcur, ranks_old, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
+                                                                                     a.d_maxgroup, a.d_sumsq, a.d_ngroups));
+            ranks_pending = false;
         }
         BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_done, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
         BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, h, a.stride, a.d_period, a.d_done, kB, vB, tiles, a.d_hist));
@@ -778,9 +802,11 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         }
         BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(nullptr, vA, rk, h, a.stride, a.d_period, a.d_done, fcur, fnext, a.d_tile_last, tiles,
                                                           a.d_ngroups));
-        BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
-                                                                              a.d_maxgroup, a.d_sumsq, a.d_ngroups));
+        BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
+                                                                                 a.d_maxgroup, a.d_sumsq, a.d_ngroups));
         std::swap(fcur, fnext);
+        ranks_pending = true;
+        ranks_old     = fnext;  // the flags of before this round
         h *= 2;
         ++rounds;
     }
