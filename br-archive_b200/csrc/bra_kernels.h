@@ -92,7 +92,9 @@ struct BwtInvArgs
     uint2*          d_walk;  // nblk * ibwt_kmax(max_n)
     uint32_t*       d_woff;  // same
     uint32_t*       d_orbit; // nblk
+    uint8_t*        d_tmp;   // optional: nblk * ibwt_kmax(max_n) * ibwt_tmp_cap(max_n) bytes -- the first walk keeps the bytes it passes
 };
+uint32_t ibwt_tmp_cap(uint32_t max_n);
 uint32_t ibwt_row_stride(uint32_t max_n);
 uint32_t ibwt_kmax(uint32_t max_n);
 bool     bwt_inverse_batch(const BwtInvArgs& a, cudaStream_t st);

@@ -826,9 +826,13 @@ __device__ __forceinline__ uint32_t ib_rows(uint32_t n, uint32_t R) { return (n 
 
 // Walk 1: from every start row (multiples of R, plus the primary row as walker K) follow
 // W[idx] >> 8 until the next start row; record the walk length and which walker it runs into.
+// With `tmp`, the walk also keeps the first `cap` bytes it passes (F[idx] = W[idx] & 0xFF) in its own scratch
+// row: walks are about R steps long, so a row of 8R bytes holds nearly every walk completely, and the output
+// can then be assembled by a sequential copy instead of a second pass of dependent random loads.
 __global__ void __launch_bounds__(IB_THREADS)
     ibwt_walk_len_kernel(const uint32_t* __restrict__ W, uint64_t stride, const uint32_t* __restrict__ len, const uint32_t* __restrict__ primary,
-                         uint32_t R, uint32_t kmax, uint2* __restrict__ walk /* (len, succ) */, uint32_t* __restrict__ woff)
+                         uint32_t R, uint32_t kmax, uint2* __restrict__ walk /* (len, succ) */, uint32_t* __restrict__ woff,
+                         uint8_t* __restrict__ tmp, uint32_t cap)
 {
     const uint32_t b = blockIdx.y;
     const uint32_t n = len[b];
@@ -840,25 +844,75 @@ __global__ void __launch_bounds__(IB_THREADS)
     const uint32_t* Wb = W + (uint64_t) b * stride;
     uint32_t idx = (w == K) ? pi : w * R;
     uint32_t steps = 0;
-    do
+    if (tmp == nullptr)
     {
-        idx = Wb[idx] >> 8;
-        ++steps;
-    } while (idx != pi && (idx % R) != 0);
+        do
+        {
+            idx = Wb[idx] >> 8;
+            ++steps;
+        } while (idx != pi && (idx % R) != 0);
+    }
+    else
+    {
+        uint4*   row = reinterpret_cast<uint4*>(tmp + ((uint64_t) b * kmax + w) * cap);  // cap is a multiple of 16
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;  // sixteen bytes gathered per store
+        do
+        {
+            const uint32_t e  = Wb[idx];
+            idx               = e >> 8;
+            const uint32_t by = (e & 0xFFu) << ((steps & 3u) * 8u);
+            const uint32_t q  = (steps >> 2) & 3u;
+            a0 |= q == 0 ? by : 0u;
+            a1 |= q == 1 ? by : 0u;
+            a2 |= q == 2 ? by : 0u;
+            a3 |= q == 3 ? by : 0u;
+            ++steps;
+            if ((steps & 15u) == 0)
+            {
+                if (steps <= cap) row[(steps >> 4) - 1] = make_uint4(a0, a1, a2, a3);
+                a0 = a1 = a2 = a3 = 0;
+            }
+        } while (idx != pi && (idx % R) != 0);
+        if ((steps & 15u) != 0 && steps <= cap) row[steps >> 4] = make_uint4(a0, a1, a2, a3);
+    }
     const uint32_t succ = (idx == pi) ? K : idx / R;
     walk[(uint64_t) b * kmax + w] = make_uint2(steps, succ);
 }
 
+// Assemble the output from the scratch rows: one warp per walk that is complete in its row.
+__global__ void __launch_bounds__(256)
+    ibwt_copy_kernel(const uint32_t* __restrict__ len, uint64_t stride, uint32_t R, uint32_t kmax, const uint2* __restrict__ walk,
+                     const uint32_t* __restrict__ woff, const uint32_t* __restrict__ orbit, const uint8_t* __restrict__ tmp, uint32_t cap,
+                     uint8_t* __restrict__ out)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = len[b];
+    if (n == 0 || orbit[b] < n) return;  // periodic blocks are replicated by the emit walk
+    const uint32_t K = ib_rows(n, R);
+    const uint32_t w = blockIdx.x * 8 + warp_id();
+    if (w > K) return;
+    const uint32_t o0 = woff[(uint64_t) b * kmax + w];
+    if (o0 == IB_INVALID) return;
+    const uint32_t steps = walk[(uint64_t) b * kmax + w].x;
+    if (steps > cap) return;  // did not fit: the emit walk does it
+    const uint8_t* row = tmp + ((uint64_t) b * kmax + w) * cap;
+    uint8_t*       ob  = out + (uint64_t) b * stride;
+    const uint32_t m   = min(steps, n - min(n, o0));
+    for (uint32_t t = lane_id(); t < m; t += 32) ob[o0 + t] = row[t];
+}
+
 // Stitch: order the walks from the primary row. If the chain closes before n bytes are covered the
 // text is a repetition of that orbit (periodic input): orbit[b] < n and every walk is replicated.
-// One CTA per block: the walk table (at most 8193 entries) is staged in shared memory so that the
-// dependent chain runs at shared-memory latency instead of one global round trip per walk.
+// One CTA per block. The successor links form a cycle through walker K (the primary row); the offset of a
+// walk is its distance from K along that cycle. It is found by pointer doubling in shared memory (about
+// log2(K) rounds over all walkers) instead of following the chain link by link.
 #define IB_STITCH_THREADS 256
+#define IB_TERM 0xFFFFFFFFu
 __global__ void __launch_bounds__(IB_STITCH_THREADS)
-    ibwt_stitch_kernel(const uint32_t* __restrict__ len, uint32_t R, uint32_t kmax, const uint2* __restrict__ walk, uint32_t* __restrict__ woff,
-                       uint32_t* __restrict__ orbit)
+    ibwt_stitch_kernel(const uint32_t* __restrict__ len, const uint32_t* __restrict__ primary, uint32_t R, uint32_t kmax,
+                       const uint2* __restrict__ walk, uint32_t* __restrict__ woff, uint32_t* __restrict__ orbit)
 {
-    extern __shared__ uint32_t s_dyn[];  // [0,kmax): walk length; [kmax,2kmax): successor; [2kmax,3kmax): offset
+    extern __shared__ uint32_t s_dyn[];  // two (distance to the end of the cycle, link) pairs of kmax words each, ping-pong
     const uint32_t b = blockIdx.x;
     const uint32_t n = len[b];
     if (n == 0)
@@ -866,38 +920,54 @@ __global__ void __launch_bounds__(IB_STITCH_THREADS)
         if (threadIdx.x == 0) orbit[b] = 0;
         return;
     }
-    const uint32_t K    = ib_rows(n, R);
-    uint32_t*      slen = s_dyn;
-    uint32_t*      ssuc = s_dyn + kmax;
-    uint32_t*      soff = s_dyn + 2 * kmax;
+    const uint32_t K  = ib_rows(n, R);
+    uint32_t*      d0 = s_dyn, *n0 = s_dyn + kmax, *d1 = s_dyn + 2 * kmax, *n1 = s_dyn + 3 * kmax;
     for (uint32_t w = threadIdx.x; w <= K; w += IB_STITCH_THREADS)
     {
         const uint2 e = walk[(uint64_t) b * kmax + w];
-        slen[w]       = e.x;
-        ssuc[w]       = e.y;
-        soff[w]       = IB_INVALID;
+        d0[w]         = e.x;
+        n0[w]         = e.y == K ? IB_TERM : e.y;  // the cycle is cut where it returns to K
     }
     __syncthreads();
-    if (threadIdx.x == 0)
+    for (uint32_t span = 1;;)  // links every pointer has jumped so far
     {
-        uint32_t w = K, o = 0;
-        while (o < n && soff[w] == IB_INVALID)
+        bool open = false;
+        for (uint32_t w = threadIdx.x; w <= K; w += IB_STITCH_THREADS)
         {
-            soff[w] = o;
-            o += slen[w];
-            w = ssuc[w];
+            const uint32_t nx = n0[w];
+            uint32_t       dd = d0[w], nn = IB_TERM;
+            if (nx != IB_TERM)
+            {
+                dd += d0[nx];  // wraps for walkers that are not on K's cycle; they are discarded below
+                nn   = n0[nx];
+                open = true;
+            }
+            d1[w] = dd;
+            n1[w] = nn;
         }
-        orbit[b] = o;  // == n unless the chain closed early
+        uint32_t* t = d0; d0 = d1; d1 = t;
+        t = n0; n0 = n1; n1 = t;
+        const bool any = __syncthreads_or(open);
+        span <<= 1;
+        // a walker on K's cycle is at most K+1 links from the cut; walkers on other cycles never reach it
+        if (!any || span > K + 1) break;
     }
-    __syncthreads();
-    for (uint32_t w = threadIdx.x; w <= K; w += IB_STITCH_THREADS) woff[(uint64_t) b * kmax + w] = soff[w];
+    const uint32_t q = d0[K];  // length of the cycle through the primary row
+    const uint32_t pi = primary[b];
+    for (uint32_t w = threadIdx.x; w <= K; w += IB_STITCH_THREADS)
+    {
+        uint32_t off = IB_INVALID;
+        if (n0[w] == IB_TERM && !(w != K && pi % R == 0 && w == pi / R)) off = q - d0[w];  // a start row equal to the primary row is walker K's double
+        woff[(uint64_t) b * kmax + w] = off;
+    }
+    if (threadIdx.x == 0) orbit[b] = q;
 }
 
 // Walk 2: emit F[idx] = W[idx] & 0xFF at the stitched offsets (replicated every `orbit` bytes).
 __global__ void __launch_bounds__(IB_THREADS)
     ibwt_walk_emit_kernel(const uint32_t* __restrict__ W, uint64_t stride, const uint32_t* __restrict__ len, const uint32_t* __restrict__ primary,
                           uint32_t R, uint32_t kmax, const uint2* __restrict__ walk, const uint32_t* __restrict__ woff,
-                          const uint32_t* __restrict__ orbit, uint8_t* __restrict__ out)
+                          const uint32_t* __restrict__ orbit, uint8_t* __restrict__ out, uint32_t cap /* 0: no scratch rows */)
 {
     const uint32_t b = blockIdx.y;
     const uint32_t n = len[b];
@@ -909,6 +979,7 @@ __global__ void __launch_bounds__(IB_THREADS)
     if (o0 == IB_INVALID) return;  // not on the primary row's orbit
     const uint32_t steps = walk[(uint64_t) b * kmax + w].x;
     const uint32_t q     = orbit[b];
+    if (cap && q >= n && steps <= cap) return;  // assembled from the scratch rows by ibwt_copy_kernel
     const uint32_t* Wb   = W + (uint64_t) b * stride;
     uint8_t*        ob   = out + (uint64_t) b * stride;
     uint32_t idx = (w == K) ? primary[b] : w * R;
@@ -953,6 +1024,7 @@ uint32_t ibwt_row_stride(uint32_t max_n)
     while ((uint64_t) R * 8192 < max_n) R *= 2;
     return R;
 }
+uint32_t ibwt_tmp_cap(uint32_t max_n) { return 8u * ibwt_row_stride(max_n); }
 uint32_t ibwt_kmax(uint32_t max_n) { return (max_n + ibwt_row_stride(max_n) - 1) / ibwt_row_stride(max_n) + 1; }
 
 static bool bwt_inverse_chunk(const BwtInvArgs& a, cudaStream_t st)
@@ -960,11 +1032,14 @@ static bool bwt_inverse_chunk(const BwtInvArgs& a, cudaStream_t st)
     const uint32_t R = ibwt_row_stride(a.max_n), kmax = ibwt_kmax(a.max_n);
     if (!radix_pass_u8_index_packed(a.d_in, a.d_W, a.stride, a.d_len, a.max_n, a.nblk, a.d_hist, st)) return false;
     const dim3 grid(bra_div_up(kmax, IB_THREADS), a.nblk);
-    BRA_LAUNCH(P_IBWT_WALK_LEN, st, ibwt_walk_len_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff));
-    const size_t stitch_smem = (size_t) kmax * 3 * sizeof(uint32_t);
-    BRA_CUDA_TRY(cudaFuncSetAttribute(ibwt_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 8200 * 4));
-    BRA_LAUNCH(P_IBWT_STITCH, st, ibwt_stitch_kernel<<<a.nblk, IB_STITCH_THREADS, stitch_smem, st>>>(a.d_len, R, kmax, a.d_walk, a.d_woff, a.d_orbit));
-    BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_walk_emit_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_out));
+    const uint32_t cap = a.d_tmp ? ibwt_tmp_cap(a.max_n) : 0u;
+    BRA_LAUNCH(P_IBWT_WALK_LEN, st, ibwt_walk_len_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_tmp, cap));
+    const size_t stitch_smem = (size_t) kmax * 4 * sizeof(uint32_t);
+    BRA_CUDA_TRY(cudaFuncSetAttribute(ibwt_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 8200 * 4));
+    BRA_LAUNCH(P_IBWT_STITCH, st, ibwt_stitch_kernel<<<a.nblk, IB_STITCH_THREADS, stitch_smem, st>>>(a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit));
+    if (cap)
+        BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_copy_kernel<<<dim3(bra_div_up(kmax, 8), a.nblk), 256, 0, st>>>(a.d_len, a.stride, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_tmp, cap, a.d_out));
+    BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_walk_emit_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_out, cap));
     BRA_CUDA_TRY(cudaGetLastError());
     return true;
 }

@@ -70,7 +70,7 @@ struct EncWs
 };
 struct DecWs
 {
-    uint8_t * R, *M, *L, *summ, *state, *sub_start, *t_exit, *t_entry;
+    uint8_t * R, *M, *L, *summ, *state, *sub_start, *t_exit, *t_entry, *wtmp;
     uint16_t* sub_count;
     uint32_t *W, *hist, *rlen, *clen, *nlen, *primary, *err, *seq_entry, *seq_exit, *seq_count, *end_bit, *changed, *t_tok, *t_ocnt, *woff,
         *orbit;
@@ -122,6 +122,7 @@ static void carve_dec(Arena& A, uint32_t S, uint32_t nb, DecWs& w)
     w.t_tok = A.take<uint32_t>(nb * rt * 32); w.t_ocnt = A.take<uint32_t>(nb * rt);
     const uint64_t km = ibwt_kmax(S);
     w.walk = A.take<uint2>(nb * km); w.woff = A.take<uint32_t>(nb * km); w.orbit = A.take<uint32_t>(nb);
+    w.wtmp = A.take<uint8_t>(nb * km * ibwt_tmp_cap(S));  // scratch rows of the inverse-BWT walks (about 8 bytes per input byte)
     w.rlen = A.take<uint32_t>(nb); w.clen = A.take<uint32_t>(nb); w.nlen = A.take<uint32_t>(nb); w.primary = A.take<uint32_t>(nb);
     w.err = A.take<uint32_t>(nb); w.end_bit = A.take<uint32_t>(nb); w.changed = A.take<uint32_t>(4);
     w.tabs = A.take<bra_huf_dec_t>(nb);
@@ -415,7 +416,7 @@ bool decode_batch(bra_b200_ctx* c, const uint8_t* d_hdr, const uint8_t* d_payloa
 
     BwtInvArgs ia{};
     ia.d_in = w.L; ia.d_out = d_out; ia.stride = S; ia.d_len = w.nlen; ia.d_primary = w.primary; ia.max_n = S; ia.nblk = nb;
-    ia.d_W = w.W; ia.d_hist = w.hist; ia.d_walk = w.walk; ia.d_woff = w.woff; ia.d_orbit = w.orbit;
+    ia.d_W = w.W; ia.d_hist = w.hist; ia.d_walk = w.walk; ia.d_woff = w.woff; ia.d_orbit = w.orbit; ia.d_tmp = w.wtmp;
     if (!bwt_inverse_batch(ia, st)) return false;
 
     if (!crc_blocks(d_out, S, w.nlen, 0, S, nb, nullptr, d_crc, st)) return false;
