@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(IB_THREADS)
         {
             idx = Wb[idx] >> 8;
             ++steps;
-        } while (idx != pi && (idx % R) != 0);
+        } while (idx != pi && (idx & (R - 1u)) != 0);  // R is a power of two
     }
     else
     {
@@ -872,7 +872,7 @@ __global__ void __launch_bounds__(IB_THREADS)
                 if (steps <= cap) row[(steps >> 4) - 1] = make_uint4(a0, a1, a2, a3);
                 a0 = a1 = a2 = a3 = 0;
             }
-        } while (idx != pi && (idx % R) != 0);
+        } while (idx != pi && (idx & (R - 1u)) != 0);  // R is a power of two
         if ((steps & 15u) != 0 && steps <= cap) row[steps >> 4] = make_uint4(a0, a1, a2, a3);
     }
     const uint32_t succ = (idx == pi) ? K : idx / R;
