@@ -71,6 +71,7 @@ struct BwtFwdArgs
     uint32_t  div_cap;
     uint8_t*  d_bad;
     uint32_t  bad_stride;
+    uint8_t*  d_alpha;  // optional, nblk*256: dense symbol codes per block -- the 4-symbol sort keys then need 4*ceil(log2(symbols)) bits only
     uint32_t* h_rounds;  // optional: number of doubling rounds executed
     // optional pinned, device-visible host words: [0,2) loop status, [2,2+div_cap) divisor values, then nblk offsets and
     // nblk counts. With it the loop's small transfers are done by copy kernels and do not queue behind bulk copies

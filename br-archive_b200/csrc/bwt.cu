@@ -95,13 +95,62 @@ __global__ void bwt_period_select_kernel(const uint32_t* __restrict__ len, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// 2. initial keys: first 4 bytes of every rotation of the primitive root, big endian
+// 2a. dense symbol codes: code[s] = number of smaller symbols present in the block. Packing the codes
+//     instead of the bytes keeps the order of the 4-symbol keys and shortens them to 4*bits(alphabet)
+//     bits: text (<= 64 symbols) sorts in 3 radix passes instead of 4, a 16-symbol alphabet in 2.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    bwt_alpha_present_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len, uint8_t* __restrict__ alpha)
+{
+    __shared__ uint8_t seen[256];
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = len[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= n) return;
+    seen[threadIdx.x] = 0;
+    __syncthreads();
+    const uint8_t* T  = in + (uint64_t) b * stride;
+    const uint32_t j0 = tile0 + threadIdx.x * 16;
+    if (j0 + 16 <= n)
+    {
+        const uint4    v    = *reinterpret_cast<const uint4*>(T + j0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 16; ++i) seen[(w[i >> 2] >> ((i & 3) * 8)) & 0xFFu] = 1;  // racing stores of the same value
+    }
+    else
+        for (uint32_t j = j0; j < n; ++j) seen[T[j]] = 1;
+    __syncthreads();
+    if (seen[threadIdx.x]) alpha[(uint64_t) b * 256 + threadIdx.x] = 1;
+}
+
+__global__ void __launch_bounds__(256) bwt_alpha_codes_kernel(uint8_t* __restrict__ alpha, uint32_t* __restrict__ max_bits)
+{
+    __shared__ uint32_t red[34];
+    const uint32_t b = blockIdx.x;
+    const uint32_t p = alpha[(uint64_t) b * 256 + threadIdx.x] ? 1u : 0u;
+    uint32_t       sigma;
+    const uint32_t code = block_excl_add(p, red, &sigma);
+    alpha[(uint64_t) b * 256 + threadIdx.x] = (uint8_t) (p ? code : 0u);
+    if (threadIdx.x == 0)
+    {
+        uint32_t bits = 1;
+        while ((1u << bits) < sigma) ++bits;
+        atomicMax(max_bits, bits);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2b. initial keys: first 4 symbols of every rotation of the primitive root, most significant first
+//     (raw bytes, or dense codes of `cbits` bits each)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t* __restrict__ in, uint64_t stride,
-                                                                   const uint32_t* __restrict__ period, uint32_t* __restrict__ keys,
-                                                                   uint32_t* __restrict__ vals, uint32_t tiles, uint32_t* __restrict__ hist)
+                                                                   const uint32_t* __restrict__ period, const uint8_t* __restrict__ alpha,
+                                                                   uint32_t cbits, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                                   uint32_t tiles, uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t sh[256];
+    __shared__ uint8_t  code[256];
     const uint32_t b = blockIdx.y;
     const uint32_t p = period[b];
     const uint32_t tile0 = blockIdx.x * EW_TILE;
@@ -111,7 +160,8 @@ __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t
         hout[(uint64_t) threadIdx.x * tiles] = 0;
         return;
     }
-    sh[threadIdx.x] = 0;
+    sh[threadIdx.x]   = 0;
+    code[threadIdx.x] = alpha ? alpha[(uint64_t) b * 256 + threadIdx.x] : (uint8_t) threadIdx.x;
     __syncthreads();
     const uint8_t* T    = in + (uint64_t) b * stride;
     const uint64_t base = (uint64_t) b * stride;
@@ -120,11 +170,11 @@ __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t
     {
         uint32_t key = 0;
         if (j + 3 < p)
-            key = ((uint32_t) T[j] << 24) | ((uint32_t) T[j + 1] << 16) | ((uint32_t) T[j + 2] << 8) | T[j + 3];
+            key = ((uint32_t) code[T[j]] << (3 * cbits)) | ((uint32_t) code[T[j + 1]] << (2 * cbits)) | ((uint32_t) code[T[j + 2]] << cbits) | code[T[j + 3]];
         else
         {
 #pragma unroll
-            for (int d = 0; d < 4; ++d) key = (key << 8) | T[(j + d) % p];
+            for (int d = 0; d < 4; ++d) key = (key << cbits) | code[T[(j + d) % p]];
         }
         keys[base + j] = key;
         vals[base + j] = j;
@@ -718,8 +768,28 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
 
     // ---- 4-byte radix sort
     uint32_t *kA = a.d_keyA, *kB = a.d_keyB, *vA = a.d_valA, *vB = a.d_valB;
-    BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, kA, vA, tiles, a.d_hist));
-    for (uint32_t shift = 0; shift < 32; shift += 8)
+    uint32_t cbits = 8;
+    if (a.d_alpha)
+    {
+        BRA_CUDA_TRY(cudaMemsetAsync(a.d_alpha, 0, (size_t) nblk * 256, st));
+        BRA_CUDA_TRY(cudaMemsetAsync(a.d_notdone, 0, 8, st));
+        BRA_LAUNCH(P_BWT_KEYS, st, bwt_alpha_present_kernel<<<grid, 256, 0, st>>>(a.d_in, a.stride, a.d_len, a.d_alpha));
+        BRA_LAUNCH(P_BWT_KEYS, st, bwt_alpha_codes_kernel<<<nblk, 256, 0, st>>>(a.d_alpha, a.d_notdone));
+        if (a.h_mail)
+        {
+            if (!mail_publish(a.h_mail, a.d_notdone, 1, st)) return false;
+            BRA_CUDA_TRY(cudaStreamSynchronize(st));
+            cbits = *reinterpret_cast<volatile uint32_t*>(a.h_mail);
+        }
+        else
+        {
+            BRA_CUDA_TRY(cudaMemcpyAsync(&cbits, a.d_notdone, 4, cudaMemcpyDeviceToHost, st));
+            BRA_CUDA_TRY(cudaStreamSynchronize(st));
+        }
+        if (cbits < 1 || cbits > 8) cbits = 8;
+    }
+    BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, a.d_alpha, cbits, kA, vA, tiles, a.d_hist));
+    for (uint32_t shift = 0; shift < 4 * cbits; shift += 8)
     {
         if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, shift, 8, /*hist_ready=*/shift == 0, a.d_hist, st)) return false;
         std::swap(kA, kB);

@@ -60,7 +60,7 @@ struct Arena
 // workspace requirement of one batch, by dry-running the carve
 struct EncWs
 {
-    uint8_t * L, *M, *R, *flags, *flags2, *bad, *done, *fin, *finskip, *summ, *state;
+    uint8_t * L, *M, *R, *flags, *flags2, *bad, *done, *fin, *finskip, *summ, *state, *alpha;
     uint32_t* maxgroup;
     unsigned long long* sumsq;
     uint32_t *keyA, *keyB, *valA, *valB, *rankA, *rankB, *hist, *len, *primary, *period, *ngroups, *notdone, *div_vals, *div_off, *div_cnt;
@@ -101,6 +101,7 @@ static void carve_enc(Arena& A, uint32_t S, uint32_t nb, EncWs& w)
     w.notdone = A.take<uint32_t>(4); w.done = A.take<uint8_t>(nb); w.fin = A.take<uint8_t>(nb); w.finskip = A.take<uint8_t>(nb);
     w.maxgroup = A.take<uint32_t>(nb); w.sumsq = A.take<unsigned long long>(nb);
     w.div_vals = A.take<uint32_t>(BRA_DIV_CAP); w.div_off = A.take<uint32_t>(nb); w.div_cnt = A.take<uint32_t>(nb);
+    w.alpha = A.take<uint8_t>((uint64_t) nb * 256);
     w.bad = A.take<uint8_t>((uint64_t) nb * BRA_BAD_STRIDE);
     w.rlen = A.take<uint32_t>(nb); w.clen = A.take<uint32_t>(nb); w.rhist = A.take<uint32_t>((uint64_t) nb * 256);
     w.codes = A.take<uint32_t>((uint64_t) nb * 256); w.ok = A.take<uint32_t>(nb);
@@ -339,7 +340,7 @@ bool encode_batch(bra_b200_ctx* c, const uint8_t* d_in, uint32_t nb, uint32_t la
     ba.d_flags = w.flags; ba.d_flags2 = w.flags2; ba.d_hist = w.hist; ba.d_tile_last = w.tile_last;
     ba.d_period = w.period; ba.d_ngroups = w.ngroups; ba.d_notdone = w.notdone; ba.d_done = w.done; ba.d_fin = w.fin; ba.d_finskip = w.finskip; ba.d_maxgroup = w.maxgroup; ba.d_sumsq = w.sumsq;
     ba.d_div_vals = w.div_vals; ba.d_div_off = w.div_off; ba.d_div_cnt = w.div_cnt; ba.div_cap = BRA_DIV_CAP;
-    ba.d_bad = w.bad; ba.bad_stride = BRA_BAD_STRIDE;
+    ba.d_bad = w.bad; ba.bad_stride = BRA_BAD_STRIDE; ba.d_alpha = w.alpha;
     uint32_t rounds = 0;
     ba.h_rounds = &rounds;
     ba.h_mail   = mail_bwt(c);
