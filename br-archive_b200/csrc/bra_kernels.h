@@ -64,13 +64,14 @@ struct BwtFwdArgs
     uint8_t * d_flags, *d_flags2;  // nblk*stride bytes each (head flags, double buffered across rounds)
     uint32_t* d_hist;     // radix_hist_bytes(max_n, nblk)
     int*      d_tile_last;  // nblk * ceil(max_n/4096)
-    uint32_t *d_period, *d_ngroups, *d_notdone /* 2 words */, *d_maxgroup;
+    uint32_t *d_period, *d_ngroups, *d_notdone /* 4 words */, *d_maxgroup;
     unsigned long long* d_sumsq;
     uint8_t * d_done, *d_fin, *d_finskip;
     uint32_t *d_div_vals, *d_div_off, *d_div_cnt;
     uint32_t  div_cap;
     uint8_t*  d_bad;
     uint32_t  bad_stride;
+    uint32_t* d_tile_heads;  // optional, nblk * ceil(max_n / 4096): with it the first doubling round sorts on dense group numbers (fewer key bits)
     uint8_t*  d_alpha;  // optional, nblk*256: dense symbol codes per block -- the 4-symbol sort keys then need 4*ceil(log2(symbols)) bits only
     uint32_t* h_rounds;  // optional: number of doubling rounds executed
     // optional pinned, device-visible host words: [0,2) loop status, [2,2+div_cap) divisor values, then nblk offsets and

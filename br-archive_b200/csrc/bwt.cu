@@ -197,7 +197,8 @@ template <int MODE>
 __global__ void __launch_bounds__(EW_THREADS)
     bwt_heads_kernel(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ sa, const uint32_t* __restrict__ rank, uint32_t h,
                      uint64_t stride, const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, const uint8_t* __restrict__ flags_old,
-                     uint8_t* __restrict__ flags, int* __restrict__ tile_last, uint32_t tiles, uint32_t* __restrict__ ngroups)
+                     uint8_t* __restrict__ flags, int* __restrict__ tile_last, uint32_t tiles, uint32_t* __restrict__ ngroups,
+                     uint32_t* __restrict__ tile_heads /* optional: heads per tile */)
 {
     __shared__ int      s_last[8];
     __shared__ uint32_t s_cnt[8];
@@ -303,7 +304,41 @@ __global__ void __launch_bounds__(EW_THREADS)
             c += s_cnt[i];
         }
         tile_last[(uint64_t) b * tiles + blockIdx.x] = L;
+        if (tile_heads) tile_heads[(uint64_t) b * tiles + blockIdx.x] = c;
         atomicAdd(&ngroups[b], c);
+    }
+}
+
+// Pass B': rank[SA[j]] = NUMBER of j's group (0, 1, 2, ... in sorted order) for every slot. Used for the first
+// doubling round only: the groups of the 4-symbol sort are few, so their numbers need fewer key bits -- and
+// radix passes -- than their positions. The order of the keys, which is all the round looks at, is the same.
+__global__ void __launch_bounds__(EW_THREADS)
+    bwt_dense_ranks_kernel(const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags, uint64_t stride, const uint32_t* __restrict__ period,
+                           const uint8_t* __restrict__ skip, const uint32_t* __restrict__ tile_heads, uint32_t tiles, uint32_t* __restrict__ rank_out,
+                           const uint32_t* __restrict__ ngroups)
+{
+    __shared__ uint32_t red[34];
+    const uint32_t b = blockIdx.y;
+    if (skip[b]) return;
+    const uint32_t p = period[b];
+    if (ngroups[b] >= p) return;  // finished: nobody will read its ranks
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= p) return;
+    const uint64_t base = (uint64_t) b * stride;
+    uint32_t       before = 0;
+    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += EW_THREADS) before += tile_heads[(uint64_t) b * tiles + t];
+    uint32_t carry;
+    block_excl_add(before, red, &carry);
+    const uint32_t j0 = tile0 + threadIdx.x * 16;
+    const uint32_t m  = j0 < p ? min(16u, p - j0) : 0u;
+    uint32_t       mask = 0;
+    for (uint32_t i = 0; i < m; ++i)
+        if (flags[base + j0 + i]) mask |= 1u << i;
+    uint32_t run = carry + block_excl_add((uint32_t) __popc(mask), red, nullptr);  // heads before my first slot
+    for (uint32_t i = 0; i < m; ++i)
+    {
+        run += (mask >> i) & 1u;
+        rank_out[base + sa[base + j0 + i]] = run - 1u;  // slot 0 is a head, so run >= 1 here
     }
 }
 
@@ -405,6 +440,7 @@ __global__ void bwt_check_done_kernel(const uint32_t* __restrict__ period, const
                                       uint8_t* __restrict__ fin, uint8_t* __restrict__ finskip, const uint32_t* __restrict__ maxgroup,
                                       const unsigned long long* __restrict__ sumsq, uint32_t* __restrict__ stat, uint32_t nblk)
 {
+    // stat[0]: blocks still sorting, stat[1]: of those, selected for the finisher, stat[2]: most groups in a block still sorting
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk) return;
     const uint8_t d = done[b];
@@ -419,6 +455,7 @@ __global__ void bwt_check_done_kernel(const uint32_t* __restrict__ period, const
         else
         {
             atomicAdd(&stat[0], 1u);
+            atomicMax(&stat[2], ngroups[b]);
             if (f == 0 && maxgroup[b] <= FIN_MAX_GROUP && sumsq[b] <= (unsigned long long) FIN_WORK_PER_ELEM * period[b])
             {
                 f = 1;
@@ -801,7 +838,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     BRA_CUDA_TRY(cudaMemsetAsync(a.d_fin, 0, nblk, st));
     BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_done, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
     BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<0><<<grid, EW_THREADS, 0, st>>>(kA, vA, nullptr, 0, a.stride, a.d_period, a.d_done, nullptr, fcur, a.d_tile_last, tiles,
-                                                      a.d_ngroups));
+                                                      a.d_ngroups, a.d_tile_heads));
     BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fcur, nullptr, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
                                                                              a.d_maxgroup, a.d_sumsq, a.d_ngroups));
     // the ranks themselves are written when (and for the blocks that) a doubling round follows
@@ -813,21 +850,21 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     while ((1ull << key_bits) < max_n) ++key_bits;
     for (;;)
     {
-        BRA_CUDA_TRY(cudaMemsetAsync(a.d_notdone, 0, 8, st));
+        BRA_CUDA_TRY(cudaMemsetAsync(a.d_notdone, 0, 16, st));
         BRA_LAUNCH(P_BWT_MISC, st, bwt_check_done_kernel<<<g1, 128, 0, st>>>(a.d_period, a.d_ngroups, a.d_done, a.d_fin, a.d_finskip, a.d_maxgroup, a.d_sumsq,
                                                                           a.d_notdone, nblk));
         BRA_LAUNCH(P_BWT_GATHER, st, bwt_gather_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, vA, a.stride, a.d_len, a.d_period, a.d_done, a.d_out, a.d_primary));
-        uint32_t stat[2] = {0, 0};
+        uint32_t stat[3] = {0, 0, 0};
         if (a.h_mail)
         {
-            if (!mail_publish(a.h_mail, a.d_notdone, 2, st)) return false;
+            // (the mail words [0,2) are followed by the divisor table, long consumed by now: three words are free to use)
+            if (!mail_publish(a.h_mail, a.d_notdone, 3, st)) return false;
             BRA_CUDA_TRY(cudaStreamSynchronize(st));
-            stat[0] = reinterpret_cast<volatile uint32_t*>(a.h_mail)[0];
-            stat[1] = reinterpret_cast<volatile uint32_t*>(a.h_mail)[1];
+            for (int i = 0; i < 3; ++i) stat[i] = reinterpret_cast<volatile uint32_t*>(a.h_mail)[i];
         }
         else
         {
-            BRA_CUDA_TRY(cudaMemcpyAsync(stat, a.d_notdone, 8, cudaMemcpyDeviceToHost, st));
+            BRA_CUDA_TRY(cudaMemcpyAsync(stat, a.d_notdone, 12, cudaMemcpyDeviceToHost, st));
             BRA_CUDA_TRY(cudaStreamSynchronize(st));
         }
         if (stat[0] == 0) break;
@@ -854,6 +891,17 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             bra_b200_log_error("bwt: prefix doubling did not converge (h=%u, max_n=%u, %u blocks left)", h, max_n, stat[0]);
             return false;
         }
+        // First round, nothing reordered by the finisher yet: sort on dense group numbers. They are below stat[2], the
+        // largest group count, which for text-like data is far below the block length -- one radix pass less.
+        const bool dense = rounds == 0 && finishes == 0 && a.d_tile_heads != nullptr;
+        uint32_t   round_bits = key_bits;
+        if (dense)
+        {
+            round_bits = 1;
+            while ((1ull << round_bits) < stat[2]) ++round_bits;
+            BRA_LAUNCH(P_BWT_RANKS, st, bwt_dense_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fcur, a.stride, a.d_period, a.d_done, a.d_tile_heads, tiles, rk, a.d_ngroups));
+            ranks_pending = false;
+        }
         if (ranks_pending)
         {
             BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<2><<<grid, EW_THREADS, 0, st>>>(vA, fcur, ranks_old, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
@@ -864,19 +912,19 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, h, a.stride, a.d_period, a.d_done, kB, vB, tiles, a.d_hist));
         std::swap(kA, kB);
         std::swap(vA, vB);
-        for (uint32_t shift = 0; shift < key_bits; shift += 8)
+        for (uint32_t shift = 0; shift < round_bits; shift += 8)
         {
             if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, shift, 8, /*hist_ready=*/shift == 0, a.d_hist, st)) return false;
             std::swap(kA, kB);
             std::swap(vA, vB);
         }
         BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(nullptr, vA, rk, h, a.stride, a.d_period, a.d_done, fcur, fnext, a.d_tile_last, tiles,
-                                                          a.d_ngroups));
+                                                          a.d_ngroups, nullptr));
         BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
                                                                                  a.d_maxgroup, a.d_sumsq, a.d_ngroups));
         std::swap(fcur, fnext);
         ranks_pending = true;
-        ranks_old     = fnext;  // the flags of before this round
+        ranks_old     = dense ? nullptr : fnext;  // the flags of before this round; after a round on group numbers every rank is rewritten
         h *= 2;
         ++rounds;
     }

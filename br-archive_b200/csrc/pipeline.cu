@@ -340,7 +340,7 @@ bool encode_batch(bra_b200_ctx* c, const uint8_t* d_in, uint32_t nb, uint32_t la
     ba.d_flags = w.flags; ba.d_flags2 = w.flags2; ba.d_hist = w.hist; ba.d_tile_last = w.tile_last;
     ba.d_period = w.period; ba.d_ngroups = w.ngroups; ba.d_notdone = w.notdone; ba.d_done = w.done; ba.d_fin = w.fin; ba.d_finskip = w.finskip; ba.d_maxgroup = w.maxgroup; ba.d_sumsq = w.sumsq;
     ba.d_div_vals = w.div_vals; ba.d_div_off = w.div_off; ba.d_div_cnt = w.div_cnt; ba.div_cap = BRA_DIV_CAP;
-    ba.d_bad = w.bad; ba.bad_stride = BRA_BAD_STRIDE; ba.d_alpha = w.alpha;
+    ba.d_bad = w.bad; ba.bad_stride = BRA_BAD_STRIDE; ba.d_alpha = w.alpha; ba.d_tile_heads = w.t_cnt;  // (the RLE stage's per-tile counters: same tiling, not in use yet)
     uint32_t rounds = 0;
     ba.h_rounds = &rounds;
     ba.h_mail   = mail_bwt(c);
