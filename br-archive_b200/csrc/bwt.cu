@@ -891,14 +891,16 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             bra_b200_log_error("bwt: prefix doubling did not converge (h=%u, max_n=%u, %u blocks left)", h, max_n, stat[0]);
             return false;
         }
-        // First round, nothing reordered by the finisher yet: sort on dense group numbers. They are below stat[2], the
-        // largest group count, which for text-like data is far below the block length -- one radix pass less.
-        const bool dense = rounds == 0 && finishes == 0 && a.d_tile_heads != nullptr;
+        // While the groups are few (stat[2] = the largest group count of a block still sorting), their dense numbers need
+        // fewer key bits -- and radix passes -- than their positions: the first round on text-like data, and most rounds
+        // of long-repeat data. (Not after a finisher pass: it moves heads without keeping the per-tile counts.)
+        uint32_t dense_bits = 1;
+        while ((1ull << dense_bits) < stat[2]) ++dense_bits;
+        const bool dense = finishes == 0 && a.d_tile_heads != nullptr && (dense_bits + 7) / 8 < (key_bits + 7) / 8;
         uint32_t   round_bits = key_bits;
         if (dense)
         {
-            round_bits = 1;
-            while ((1ull << round_bits) < stat[2]) ++round_bits;
+            round_bits = dense_bits;
             BRA_LAUNCH(P_BWT_RANKS, st, bwt_dense_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fcur, a.stride, a.d_period, a.d_done, a.d_tile_heads, tiles, rk, a.d_ngroups));
             ranks_pending = false;
         }
@@ -919,7 +921,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             std::swap(vA, vB);
         }
         BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(nullptr, vA, rk, h, a.stride, a.d_period, a.d_done, fcur, fnext, a.d_tile_last, tiles,
-                                                          a.d_ngroups, nullptr));
+                                                          a.d_ngroups, a.d_tile_heads));
         BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
                                                                                  a.d_maxgroup, a.d_sumsq, a.d_ngroups));
         std::swap(fcur, fnext);
