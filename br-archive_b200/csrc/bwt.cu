@@ -146,8 +146,8 @@ __global__ void __launch_bounds__(256) bwt_alpha_codes_kernel(uint8_t* __restric
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t* __restrict__ in, uint64_t stride,
                                                                    const uint32_t* __restrict__ period, const uint8_t* __restrict__ alpha,
-                                                                   uint32_t cbits, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                                   uint32_t tiles, uint32_t* __restrict__ hist)
+                                                                   uint32_t cbits, uint32_t* __restrict__ keys, uint32_t tiles,
+                                                                   uint32_t* __restrict__ hist)
 {
     __shared__ uint32_t sh[256];
     __shared__ uint8_t  code[256];
@@ -177,7 +177,6 @@ __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t
             for (int d = 0; d < 4; ++d) key = (key << cbits) | code[T[(j + d) % p]];
         }
         keys[base + j] = key;
-        vals[base + j] = j;
         atomicAdd(&sh[key & 0xFFu], 1u);
     }
     __syncthreads();
@@ -825,10 +824,11 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         }
         if (cbits < 1 || cbits > 8) cbits = 8;
     }
-    BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, a.d_alpha, cbits, kA, vA, tiles, a.d_hist));
+    BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, a.d_alpha, cbits, kA, tiles, a.d_hist));
     for (uint32_t shift = 0; shift < 4 * cbits; shift += 8)
     {
-        if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, shift, 8, /*hist_ready=*/shift == 0, a.d_hist, st)) return false;
+        // the first pass takes the rotation indices as implicit values
+        if (!radix_pass_u32(kA, shift == 0 ? nullptr : vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, shift, 8, /*hist_ready=*/shift == 0, a.d_hist, st)) return false;
         std::swap(kA, kB);
         std::swap(vA, vB);
     }

@@ -266,6 +266,8 @@ bool radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_o
                     bool hist_ready, uint32_t* d_hist, cudaStream_t st)
 {
     (void) bits;  // only the 8-bit digit is instantiated
+    if (vals == nullptr)  // values are the element indices 0, 1, 2, ... (first pass of a sort): nothing to read
+        return radix_pass_t<8, uint32_t, true, 0>(keys, nullptr, keys_out, vals_out, stride, d_len, d_skip, max_len, nblk, shift, hist_ready, d_hist, st);
     return radix_pass_t<8, uint32_t, false, 0>(keys, vals, keys_out, vals_out, stride, d_len, d_skip, max_len, nblk, shift, hist_ready, d_hist, st);
 }
 
