@@ -190,18 +190,17 @@ __global__ void __launch_bounds__(MTF_WARPS * 32)
     int*           last = s_last[w];
     for (int i = lane; i < 256; i += 32) last[i] = -1;
     __syncwarp();
-    for (uint32_t i = lane * 4; i < m; i += 128)
+    // 32 consecutive positions per step, one per lane: of the lanes that hold the same symbol the highest one has the
+    // latest position and stores it (a plain store; BWT output is long runs of one symbol, on which an atomicMax per
+    // byte serialises the warp). Later steps overwrite earlier ones in program order.
+    for (uint32_t i0 = 0; i0 < m; i0 += 32)
     {
-        if (i + 4 <= m)
-        {
-            const uint32_t v = *reinterpret_cast<const uint32_t*>(p + i);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) atomicMax(&last[(v >> (8 * k)) & 0xFFu], (int) (i + k));
-        }
-        else
-            for (uint32_t k = 0; i + k < m; ++k) atomicMax(&last[p[i + k]], (int) (i + k));
+        const uint32_t i   = i0 + lane;
+        const uint32_t sym = i < m ? (uint32_t) p[i] : (0x100u | lane);  // padding matches nothing
+        const uint32_t peers = __match_any_sync(BRA_FULL, sym);
+        if (i < m && lane == 31u - (uint32_t) __clz(peers)) last[sym] = (int) i;
+        __syncwarp();
     }
-    __syncwarp();
     // rank each present symbol by counting symbols with a later last occurrence
     uint8_t* o = summ + ((uint64_t) b * segs + seg) * 256;
     uint32_t present = 0;

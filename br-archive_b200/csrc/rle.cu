@@ -562,21 +562,37 @@ __global__ void __launch_bounds__(RD_THREADS)
     if (threadIdx.x == 0) tstart[ntok] = mine;
     __syncthreads();
 
-    uint8_t* ob = out + (uint64_t) b * out_stride + out0;
-    for (uint32_t o = threadIdx.x; o < mine; o += RD_THREADS)
+    // Four consecutive output bytes per thread: one binary search for the first, then the token list is walked
+    // forward, and the four bytes leave as one aligned 32-bit store (groups are aligned to the output address).
+    uint8_t*       ob  = out + (uint64_t) b * out_stride + out0;
+    const uint32_t mis = (uint32_t) (reinterpret_cast<uintptr_t>(ob) & 3u);
+    const uint32_t ngroups = (mine + mis + 3) / 4;
+    for (uint32_t g = threadIdx.x; g < ngroups; g += RD_THREADS)
     {
-        uint32_t lo = 0, hi = ntok;  // last token with tstart <= o
+        const uint32_t o_begin = g * 4 >= mis ? g * 4 - mis : 0u;
+        const uint32_t o_end   = min(mine, g * 4 + 4 - mis);
+        uint32_t lo = 0, hi = ntok;  // last token with tstart <= o_begin
         while (hi - lo > 1)
         {
             const uint32_t mid = (lo + hi) >> 1;
-            if (tstart[mid] <= o)
+            if (tstart[mid] <= o_begin)
                 lo = mid;
             else
                 hi = mid;
         }
-        const uint32_t src = tile0 + tsrc[lo];
-        const int8_t   c   = (int8_t) xb[src];
-        ob[o]              = c >= 0 ? xb[src + 1 + (o - tstart[lo])] : xb[src + 1];
+        uint32_t acc = 0;
+        for (uint32_t o = o_begin; o < o_end; ++o)
+        {
+            while (tstart[lo + 1] <= o) ++lo;  // tstart[ntok] == mine > o ends the walk
+            const uint32_t src = tile0 + tsrc[lo];
+            const int8_t   c   = (int8_t) xb[src];
+            const uint32_t v   = c >= 0 ? xb[src + 1 + (o - tstart[lo])] : xb[src + 1];
+            acc |= v << ((o - o_begin) * 8u);
+        }
+        if (o_end - o_begin == 4)
+            *reinterpret_cast<uint32_t*>(ob + o_begin) = acc;
+        else
+            for (uint32_t o = o_begin; o < o_end; ++o) ob[o] = (uint8_t) (acc >> ((o - o_begin) * 8u));
     }
 }
 
