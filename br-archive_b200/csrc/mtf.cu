@@ -190,17 +190,23 @@ __global__ void __launch_bounds__(MTF_WARPS * 32)
     int*           last = s_last[w];
     for (int i = lane; i < 256; i += 32) last[i] = -1;
     __syncwarp();
-    // 32 consecutive positions per step, one per lane: of the lanes that hold the same symbol the highest one has the
-    // latest position and stores it (a plain store; BWT output is long runs of one symbol, on which an atomicMax per
-    // byte serialises the warp). Later steps overwrite earlier ones in program order.
-    for (uint32_t i0 = 0; i0 < m; i0 += 32)
+    for (uint32_t i = lane * 4; i < m; i += 128)
     {
-        const uint32_t i   = i0 + lane;
-        const uint32_t sym = i < m ? (uint32_t) p[i] : (0x100u | lane);  // padding matches nothing
-        const uint32_t peers = __match_any_sync(BRA_FULL, sym);
-        if (i < m && lane == 31u - (uint32_t) __clz(peers)) last[sym] = (int) i;
-        __syncwarp();
+        if (i + 4 <= m)
+        {
+            // a byte whose symbol occurs again later in the same word cannot be the last occurrence: BWT output is
+            // mostly runs, so this removes most of the atomics (and of their same-address serialisation)
+            const uint32_t v  = *reinterpret_cast<const uint32_t*>(p + i);
+            const uint32_t b0 = v & 0xFFu, b1 = (v >> 8) & 0xFFu, b2 = (v >> 16) & 0xFFu, b3 = v >> 24;
+            atomicMax(&last[b3], (int) (i + 3));
+            if (b2 != b3) atomicMax(&last[b2], (int) (i + 2));
+            if (b1 != b2 && b1 != b3) atomicMax(&last[b1], (int) (i + 1));
+            if (b0 != b1 && b0 != b2 && b0 != b3) atomicMax(&last[b0], (int) i);
+        }
+        else
+            for (uint32_t k = 0; i + k < m; ++k) atomicMax(&last[p[i + k]], (int) (i + k));
     }
+    __syncwarp();
     // rank each present symbol by counting symbols with a later last occurrence
     uint8_t* o = summ + ((uint64_t) b * segs + seg) * 256;
     uint32_t present = 0;
