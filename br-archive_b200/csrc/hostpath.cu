@@ -118,6 +118,22 @@ __global__ void compact_out_kernel(const uint8_t* __restrict__ src, uint32_t blo
 
 }  // namespace
 
+// page-locked host memory for callers that have no CUDA headers (the seam's window buffers)
+extern "C" void* bra_b200_host_alloc(uint64_t bytes)
+{
+    void* p = nullptr;
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess)
+    {
+        cudaGetLastError();  // a failed allocation must not poison the next call
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void bra_b200_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" uint64_t bra_b200_encode_bound(const bra_b200_ctx_t* c, uint64_t total)
 {
     if (!c) return 0;

@@ -48,6 +48,35 @@ static bra_b200_ctx_t* b200_ctx(void)
     return g_b200_ctx;
 }
 
+/* Window buffers: page-locked (the GPU copies run at the full PCIe rate from and to them) and kept between calls,
+ * like the reference's own g_buf scratch (lib_bra.c:25-45). [0] = plain side, [1] = chunk-stream side.
+ * If page-locking fails they are ordinary memory: slower copies, same results. */
+typedef struct
+{
+    uint8_t* p;
+    uint64_t cap;
+    bool     pinned;
+} b200_window_t;
+static b200_window_t g_window[2];
+
+static uint8_t* b200_window(const int which, const uint64_t bytes)
+{
+    b200_window_t* w = &g_window[which];
+    if (w->p != NULL && w->cap >= bytes) return w->p;
+    if (w->p != NULL)
+    {
+        if (w->pinned)
+            bra_b200_host_free(w->p);
+        else
+            free(w->p);
+    }
+    w->p      = bra_b200_host_alloc(bytes);
+    w->pinned = w->p != NULL;
+    if (w->p == NULL) w->p = malloc(bytes);
+    w->cap = w->p != NULL ? bytes : 0;
+    return w->p;
+}
+
 static bool chunk_header_is_valid(const uint8_t* disk_hdr) /* chunks.c:31-48 on the 267-byte disk image */
 {
     const uint32_t pi = (uint32_t) disk_hdr[0] | ((uint32_t) disk_hdr[1] << 8) | ((uint32_t) disk_hdr[2] << 16);
@@ -165,8 +194,8 @@ bool bra_io_file_chunks_compress_file(bra_io_file_t* dst, bra_io_file_t* src, co
     }
     const uint64_t in_cap  = data_size < window ? (data_size ? data_size : 1) : window;
     const uint64_t out_cap = bra_b200_encode_bound(ctx, in_cap);
-    in  = malloc(in_cap);
-    out = malloc(out_cap ? out_cap : 1);
+    in  = b200_window(0, in_cap);
+    out = b200_window(1, out_cap ? out_cap : 1);
     if (in == NULL || out == NULL) goto fail;
 
     for (uint64_t i = 0; i < data_size;)
@@ -178,8 +207,6 @@ bool bra_io_file_chunks_compress_file(bra_io_file_t* dst, bra_io_file_t* src, co
         {
             bra_io_file_close(&tmpfile);
             bra_io_file_close(dst);
-            free(in);
-            free(out);
             return false;
         }
         uint64_t out_size = 0;
@@ -214,14 +241,10 @@ bool bra_io_file_chunks_compress_file(bra_io_file_t* dst, bra_io_file_t* src, co
         res = bra_io_file_chunks_copy_file(dst, &tmpfile, tmpfile_size, me, false);
     }
     bra_io_file_close(&tmpfile);
-    free(in);
-    free(out);
     return res;
 
 fail:
     bra_io_file_close(&tmpfile);
-    free(in);
-    free(out);
     bra_io_file_close(dst);
     bra_io_file_close(src);
     return false;
@@ -243,8 +266,8 @@ bool bra_io_file_chunks_decompress_file(bra_io_file_t* dst, bra_io_file_t* src, 
 
     if (dst != NULL && (dst->f == NULL || dst->fn == NULL)) goto fail;
     const uint64_t stream_cap = data_size < max_stream ? (data_size ? data_size : 1) : max_stream;
-    stream = malloc(stream_cap);
-    if (decode) plain = malloc((size_t) _bra_min((uint64_t) B200_WINDOW_CHUNKS, data_size / BRA_IO_CHUNK_HEADER_SIZE + 1) * BRA_MAX_CHUNK_SIZE);
+    stream = b200_window(1, stream_cap);
+    if (decode) plain = b200_window(0, _bra_min((uint64_t) B200_WINDOW_CHUNKS, data_size / BRA_IO_CHUNK_HEADER_SIZE + 1) * BRA_MAX_CHUNK_SIZE);
     if (stream == NULL || (decode && plain == NULL)) goto fail;
 
     for (uint64_t i = 0; i < data_size;)
@@ -307,13 +330,9 @@ bool bra_io_file_chunks_decompress_file(bra_io_file_t* dst, bra_io_file_t* src, 
         goto fail;
     }
     me->_compression_ratio = (float) ((double) data_size / (double) file_orig_size);
-    free(stream);
-    free(plain);
     return true;
 
 fail:
-    free(stream);
-    free(plain);
     if (dst != NULL) bra_io_file_close(dst);
     bra_io_file_close(src);
     return false;

@@ -85,6 +85,12 @@ int bra_b200_decode_host(bra_b200_ctx_t* ctx, const uint8_t* in, uint64_t in_siz
  * makes its chunk count as 0 bytes. */
 int bra_b200_list_host(bra_b200_ctx_t* ctx, const uint8_t* in, uint64_t in_size, uint64_t* plain_size);
 
+/* Page-locked host memory for the buffers handed to the three calls above: copies to and from it run at the
+ * full PCIe rate and overlap the kernels (ordinary memory works too, at a fraction of the rate).
+ * bra_b200_host_alloc returns NULL when the memory cannot be locked. */
+void* bra_b200_host_alloc(uint64_t bytes);
+void  bra_b200_host_free(void* p);
+
 /* ---- launch accounting (process-wide; used by bench.py for `gpu_launches` and the roofline) ----
  * Every kernel launch of the library is counted per kernel family. With timing enabled each launch is
  * also bracketed by CUDA events on its own stream; the accumulated device time is read back lazily. */
