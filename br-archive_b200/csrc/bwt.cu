@@ -343,8 +343,8 @@ __global__ void __launch_bounds__(EW_THREADS)
 
 // Pass B: rank[SA[j]] = index of the head of j's group, in place. Slots that were singleton groups
 // before this round (flags_old) keep their rank and are not touched.
-// WHAT 0: ranks and group statistics; 1: statistics only (the ranks are written later, and only if the
-// block goes on doubling -- a block the finisher completes never reads them); 2: ranks only.
+// WHAT 1: group statistics only (the ranks are written later, and only if the block goes on doubling -- a block the
+// finisher completes never reads them); WHAT 2: ranks only.
 template <int WHAT>
 __global__ void __launch_bounds__(EW_THREADS)
     bwt_ranks_kernel(const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ flags_old, uint64_t stride,

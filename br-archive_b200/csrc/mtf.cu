@@ -101,7 +101,6 @@ __device__ __forceinline__ uint32_t lane_mtf_encode(uint4* Q, uint32_t x)
 // symbol ("relative symbol"), and the final list is the position permutation of the segment (its summary).
 // After the per-block scan has produced the entry lists, mtf_map_kernel turns relative symbols into symbols
 // with a 256-entry table lookup -- so decoding replays each segment once, not twice.
-// (MODE 1, decode from a known entry list, is kept for completeness; the batch path does not use it.)
 template <int MODE>
 __global__ void __launch_bounds__(MTF_LANE_WARPS * 32)
     mtf_lane_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, uint64_t stride, const uint32_t* __restrict__ len, uint32_t segs,
