@@ -399,9 +399,11 @@ def test_reference_unit_test_programs_pass_against_the_dropin(golden, tmp_path):
 
 def test_batched_fuzz_shapes(pkg, oracle, vocab):
     """Many small batches with odd block sizes, ragged tails and mixed content, every block compared with the oracle."""
-    rng = random.Random(12)
-    nrng = np.random.default_rng(12)
-    for it in range(18):
+    import os
+    seed = int(os.environ.get("BRA_FUZZ_SEED", "12"))  # BRA_FUZZ_SEED / BRA_FUZZ_ITERS: longer campaigns by hand
+    rng = random.Random(seed)
+    nrng = np.random.default_rng(seed)
+    for it in range(int(os.environ.get("BRA_FUZZ_ITERS", "18"))):
         block = rng.choice([16, 48, 256, 4096, 4112, 8192 + 16, 12288, 20000 - 20000 % 16])
         nblk = rng.choice([1, 2, 3, 5, 9])
         tail = rng.randrange(1, block + 1)
