@@ -23,6 +23,7 @@
 #include "bra_common.cuh"
 #include "bra_kernels.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -437,7 +438,7 @@ __global__ void __launch_bounds__(EW_THREADS)
 
 __global__ void bwt_check_done_kernel(const uint32_t* __restrict__ period, const uint32_t* __restrict__ ngroups, uint8_t* __restrict__ done,
                                       uint8_t* __restrict__ fin, uint8_t* __restrict__ finskip, const uint32_t* __restrict__ maxgroup,
-                                      const unsigned long long* __restrict__ sumsq, uint32_t* __restrict__ stat, uint32_t nblk)
+                                      const unsigned long long* __restrict__ sumsq, uint32_t* __restrict__ stat, uint32_t nblk, bool allow_finisher)
 {
     // stat[0]: blocks still sorting, stat[1]: of those, selected for the finisher, stat[2]: most groups in a block still sorting
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -455,7 +456,7 @@ __global__ void bwt_check_done_kernel(const uint32_t* __restrict__ period, const
         {
             atomicAdd(&stat[0], 1u);
             atomicMax(&stat[2], ngroups[b]);
-            if (f == 0 && maxgroup[b] <= FIN_MAX_GROUP && sumsq[b] <= (unsigned long long) FIN_WORK_PER_ELEM * period[b])
+            if (allow_finisher && f == 0 && maxgroup[b] <= FIN_MAX_GROUP && sumsq[b] <= (unsigned long long) FIN_WORK_PER_ELEM * period[b])
             {
                 f = 1;
                 atomicAdd(&stat[1], 1u);
@@ -521,7 +522,11 @@ __device__ __forceinline__ int rot_cmp_window(const uint8_t* __restrict__ T, uin
     uint32_t k = 0;
     while (k < FIN_DEPTH)
     {
-        if (ia + 8 <= p && ic + 8 <= p)  // both windows (plus the second word of the unaligned read) stay inside the block
+        // Word steps only while they stay inside the window: after byte steps (a window that wraps around the block end) k
+        // is no multiple of four any more, and a word compared at k = 61..63 would look 1-3 bytes past FIN_DEPTH. Every
+        // pair must be compared to exactly the same depth, or "equal" stops being transitive and two members of a group
+        // can be counted into the same slot.
+        if (k + 4 <= FIN_DEPTH && ia + 8 <= p && ic + 8 <= p)  // (plus the second word of the unaligned read stays inside the block)
         {
             const uint32_t x = load_be32(T, ia), y = load_be32(T, ic);
             if (x != y) return x < y ? -1 : 1;
@@ -804,8 +809,11 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
 
     // ---- 4-byte radix sort
     uint32_t *kA = a.d_keyA, *kB = a.d_keyB, *vA = a.d_valA, *vB = a.d_valB;
+    // diagnostic switches (parity triage): each turns one optional optimisation off
+    const bool no_alpha = getenv("BRA_B200_NO_ALPHA") != nullptr, no_dense = getenv("BRA_B200_NO_DENSE") != nullptr,
+               no_finish = getenv("BRA_B200_NO_FINISH") != nullptr;
     uint32_t cbits = 8;
-    if (a.d_alpha)
+    if (a.d_alpha && !no_alpha)
     {
         BRA_CUDA_TRY(cudaMemsetAsync(a.d_alpha, 0, (size_t) nblk * 256, st));
         BRA_CUDA_TRY(cudaMemsetAsync(a.d_notdone, 0, 8, st));
@@ -824,7 +832,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         }
         if (cbits < 1 || cbits > 8) cbits = 8;
     }
-    BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, a.d_alpha, cbits, kA, tiles, a.d_hist));
+    BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, no_alpha ? nullptr : a.d_alpha, cbits, kA, tiles, a.d_hist));
     for (uint32_t shift = 0; shift < 4 * cbits; shift += 8)
     {
         // the first pass takes the rotation indices as implicit values
@@ -852,7 +860,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     {
         BRA_CUDA_TRY(cudaMemsetAsync(a.d_notdone, 0, 16, st));
         BRA_LAUNCH(P_BWT_MISC, st, bwt_check_done_kernel<<<g1, 128, 0, st>>>(a.d_period, a.d_ngroups, a.d_done, a.d_fin, a.d_finskip, a.d_maxgroup, a.d_sumsq,
-                                                                          a.d_notdone, nblk));
+                                                                          a.d_notdone, nblk, !no_finish));
         BRA_LAUNCH(P_BWT_GATHER, st, bwt_gather_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, vA, a.stride, a.d_len, a.d_period, a.d_done, a.d_out, a.d_primary));
         uint32_t stat[3] = {0, 0, 0};
         if (a.h_mail)
@@ -896,7 +904,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         // of long-repeat data. (Not after a finisher pass: it moves heads without keeping the per-tile counts.)
         uint32_t dense_bits = 1;
         while ((1ull << dense_bits) < stat[2]) ++dense_bits;
-        const bool dense = finishes == 0 && a.d_tile_heads != nullptr && (dense_bits + 7) / 8 < (key_bits + 7) / 8;
+        const bool dense = !no_dense && finishes == 0 && a.d_tile_heads != nullptr && (dense_bits + 7) / 8 < (key_bits + 7) / 8;
         uint32_t   round_bits = key_bits;
         if (dense)
         {

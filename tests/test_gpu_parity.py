@@ -426,7 +426,31 @@ def test_batched_fuzz_shapes(pkg, oracle, vocab):
             rep = nrng.integers(0, 256, q, dtype=np.uint8).tobytes()
             data = (_text(pkg, vocab, block, seed=it) + rep * 3 + nrng.integers(0, 256, block, dtype=np.uint8).tobytes() + rep[: q // 2] * 7) * nblk
             data = data[:n]
-        _check_batch(pkg, oracle, data, block, max_batch=rng.choice([1, 2, 4, 16]))
+        mb = rng.choice([1, 2, 4, 16])
+        try:
+            _check_batch(pkg, oracle, data, block, max_batch=mb)
+        except AssertionError:
+            # keep the failing case for study off the GPU box
+            out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+            os.makedirs(out_dir, exist_ok=True)
+            with open(os.path.join(out_dir, "fuzz_fail.json"), "w") as f:
+                import json
+                json.dump({"seed": seed, "it": it, "kind": kind, "block": block, "nblk": nblk, "n": n, "max_batch": mb, "data": data.hex()}, f)
+            raise
+
+
+def test_bwt_finisher_compares_every_pair_to_the_same_depth(pkg, oracle):
+    """Regression (found by a 3000-round fuzz campaign, seed 31337, round 608): a block of long runs whose last 255-member
+    group reaches the BWT finisher at h = 4096 with comparison windows that wrap around the block end. The wrapped
+    windows were compared 1-3 bytes deeper than the others, "equal" stopped being transitive and two rotations were
+    counted into the same slot (primary index 5639 instead of 5644). tools/fuzz_probe.py replays the same case with each
+    optional BWT optimisation switched off."""
+    import json
+    import os
+    case = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_case_31337_608.json")))
+    data = bytes.fromhex(case["data"])
+    _check_batch(pkg, oracle, data, case["block"], max_batch=case["max_batch"])
+    _check_batch(pkg, oracle, data[case["block"]:], case["block"], max_batch=1)  # the failing block alone
 
 
 # ------------------------------------------------------------------------------------------ the reference CLI as a drop-in
