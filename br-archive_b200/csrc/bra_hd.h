@@ -260,6 +260,83 @@ BRA_HD uint32_t bra_huf_decode_one(const bra_huf_dec_t* d, uint32_t w, uint8_t* 
     return 0;
 }
 
+// ---- BWT finisher: compare two rotations of T (period p) over the `depth` bytes that start `from` bytes in ----------
+// (`from` already reduced mod p; depth a multiple of 4; T 4-byte aligned). Four bytes per step through aligned word
+// loads while neither side is about to wrap around the block end, bytes otherwise. EVERY pair is compared to exactly
+// `depth` bytes: a deeper look at some pairs only would make "equal" non-transitive, and the finisher's counting sort
+// would put two members of a group into the same slot.
+BRA_HD uint32_t bra_funnel_r(uint32_t lo, uint32_t hi, uint32_t s)
+{
+#ifdef __CUDA_ARCH__
+    return __funnelshift_r(lo, hi, s);
+#else
+    return (uint32_t) ((((uint64_t) hi << 32) | lo) >> (s & 31u));
+#endif
+}
+BRA_HD uint32_t bra_bswap32(uint32_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(x, 0, 0x0123);
+#else
+    return __builtin_bswap32(x);
+#endif
+}
+BRA_HD uint32_t bra_load_be32(const uint8_t* T, uint32_t i)  // bytes i..i+3, first byte most significant
+{
+    const uint32_t* Tw = reinterpret_cast<const uint32_t*>(T);
+    const uint32_t  w0 = Tw[i >> 2], w1 = Tw[(i >> 2) + 1];
+    return bra_bswap32(bra_funnel_r(w0, w1, (i & 3u) * 8));
+}
+BRA_HD int bra_rot_cmp_window(const uint8_t* T, uint32_t p, uint32_t a, uint32_t c, uint32_t from, uint32_t depth)
+{
+    uint32_t ia = a + from, ic = c + from;
+    if (ia >= p) ia -= p;
+    if (ic >= p) ic -= p;
+    if (ia + depth + 4u <= p && ic + depth + 4u <= p)
+    {
+        // neither window wraps: stream aligned words, one new word per side and step
+        const uint32_t* Ta = reinterpret_cast<const uint32_t*>(T) + (ia >> 2);
+        const uint32_t* Tc = reinterpret_cast<const uint32_t*>(T) + (ic >> 2);
+        const uint32_t  sa = (ia & 3u) * 8u, sc = (ic & 3u) * 8u;
+        uint32_t        a0 = Ta[0], c0 = Tc[0];
+#ifdef __CUDA_ARCH__
+#pragma unroll 4
+#endif
+        for (uint32_t k = 1; k <= depth / 4u; ++k)
+        {
+            const uint32_t a1 = Ta[k], c1 = Tc[k];
+            const uint32_t x = bra_funnel_r(a0, a1, sa), y = bra_funnel_r(c0, c1, sc);  // bytes in memory order, first byte lowest
+            if (x != y) return bra_bswap32(x) < bra_bswap32(y) ? -1 : 1;
+            a0 = a1;
+            c0 = c1;
+        }
+        return 0;
+    }
+    uint32_t k = 0;
+    while (k < depth)
+    {
+        // word steps only while they stay inside the window (after byte steps k is no multiple of four any more), and while
+        // the second word of the unaligned read stays inside the block
+        if (k + 4 <= depth && ia + 8 <= p && ic + 8 <= p)
+        {
+            const uint32_t x = bra_load_be32(T, ia), y = bra_load_be32(T, ic);
+            if (x != y) return x < y ? -1 : 1;
+            ia += 4;
+            ic += 4;
+            k += 4;
+        }
+        else
+        {
+            const uint8_t x = T[ia], y = T[ic];
+            if (x != y) return x < y ? -1 : 1;
+            if (++ia == p) ia = 0;
+            if (++ic == p) ic = 0;
+            ++k;
+        }
+    }
+    return 0;
+}
+
 // ---- host-path pipeline: blocks per stage ------------------------------------------------------------------------
 // Every stage costs a few milliseconds of latency-bound kernels whatever its size; the input copy of a stage hides
 // behind the kernels of the stage before it and its output copy behind those of the stage after it, so only the

@@ -21,6 +21,7 @@
 //   (and at the primary row) and stop at the next start row; a per-block stitch orders the
 //   walks from the primary row and a second walk writes the bytes at their final offsets.
 #include "bra_common.cuh"
+#include "bra_hd.h"
 #include "bra_kernels.h"
 
 #include <stdlib.h>
@@ -487,63 +488,11 @@ __global__ void bwt_reset_tile_last_kernel(const uint8_t* __restrict__ skip, int
 // directly (bytes h .. h+FIN_DEPTH-1; everything before is known equal). Every member counts the
 // members that sort before it, so the kernel is fully parallel. Members still equal after FIN_DEPTH
 // bytes stay one group (in their current order) and go on with prefix doubling.
-// Compares rotations a and c over bytes [from, from+FIN_DEPTH) (from already reduced mod p); four bytes per
-// step through aligned word loads while neither side is about to wrap, bytes otherwise.
-__device__ __forceinline__ uint32_t load_be32(const uint8_t* __restrict__ T, uint32_t i)
-{
-    const uint32_t* Tw = reinterpret_cast<const uint32_t*>(T);
-    const uint32_t  w0 = Tw[i >> 2], w1 = Tw[(i >> 2) + 1];
-    return __byte_perm(__funnelshift_r(w0, w1, (i & 3u) * 8), 0, 0x0123);  // bytes i..i+3, first byte most significant
-}
-
+// The comparison itself is bra_rot_cmp_window (bra_hd.h): shared with the host so that the CPU suite can check it,
+// wrap-around cases included, against a plain byte comparison.
 __device__ __forceinline__ int rot_cmp_window(const uint8_t* __restrict__ T, uint32_t p, uint32_t a, uint32_t c, uint32_t from)
 {
-    uint32_t ia = a + from, ic = c + from;
-    if (ia >= p) ia -= p;
-    if (ic >= p) ic -= p;
-    if (ia + FIN_DEPTH + 4u <= p && ic + FIN_DEPTH + 4u <= p)
-    {
-        // neither window wraps: stream aligned words, one new word per side and step (T is 16-byte aligned)
-        const uint32_t* Ta = reinterpret_cast<const uint32_t*>(T) + (ia >> 2);
-        const uint32_t* Tc = reinterpret_cast<const uint32_t*>(T) + (ic >> 2);
-        const uint32_t  sa = (ia & 3u) * 8u, sc = (ic & 3u) * 8u;
-        uint32_t        a0 = Ta[0], c0 = Tc[0];
-#pragma unroll 4
-        for (uint32_t k = 1; k <= FIN_DEPTH / 4u; ++k)
-        {
-            const uint32_t a1 = Ta[k], c1 = Tc[k];
-            const uint32_t x = __funnelshift_r(a0, a1, sa), y = __funnelshift_r(c0, c1, sc);  // bytes in memory order, first byte lowest
-            if (x != y) return __byte_perm(x, 0, 0x0123) < __byte_perm(y, 0, 0x0123) ? -1 : 1;
-            a0 = a1;
-            c0 = c1;
-        }
-        return 0;
-    }
-    uint32_t k = 0;
-    while (k < FIN_DEPTH)
-    {
-        // Word steps only while they stay inside the window: after byte steps (a window that wraps around the block end) k
-        // is no multiple of four any more, and a word compared at k = 61..63 would look 1-3 bytes past FIN_DEPTH. Every
-        // pair must be compared to exactly the same depth, or "equal" stops being transitive and two members of a group
-        // can be counted into the same slot.
-        if (k + 4 <= FIN_DEPTH && ia + 8 <= p && ic + 8 <= p)  // (plus the second word of the unaligned read stays inside the block)
-        {
-            const uint32_t x = load_be32(T, ia), y = load_be32(T, ic);
-            if (x != y) return x < y ? -1 : 1;
-            ia += 4;
-            ic += 4;
-            k += 4;
-        }
-        else
-        {
-            const uint8_t x = T[ia], y = T[ic];
-            if (x != y) return x < y ? -1 : 1;
-            if (++ia == p) ia = 0;
-            if (++ic == p) ic = 0;
-            ++k;
-        }
-    }
-    return 0;
+    return bra_rot_cmp_window(T, p, a, c, from, FIN_DEPTH);
 }
 
 // Slots that are singleton groups already (most of them) are copied through; the members of the remaining

@@ -61,6 +61,9 @@ int hl_huf_decode(const uint8_t* lengths, const uint8_t* data, uint32_t nbytes, 
     return 0;
 }
 
+// BWT finisher comparison (bra_rot_cmp_window); T must be 4-byte aligned and readable up to p rounded up to 4
+int hl_rot_cmp(const uint8_t* T, uint32_t p, uint32_t a, uint32_t c, uint32_t from, uint32_t depth) { return bra_rot_cmp_window(T, p, a, c, from, depth); }
+
 // host-path pipeline plan (bra_stage_plan); `plan` must hold nblk / hb + 4 entries
 uint32_t hl_stage_plan(uint64_t nblk, uint32_t hb, uint32_t* plan) { return bra_stage_plan(nblk, hb, plan); }
 

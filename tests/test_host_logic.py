@@ -123,3 +123,40 @@ def test_stage_plan_covers_every_block(hl):
     plan = np.zeros(8, dtype=np.uint32)
     k = hl.hl_stage_plan(1024, 1024, plan.ctypes.data_as(u32p))
     assert plan[:k].tolist() == [102, 602, 256, 64]  # short head, wide middle, shrinking tail
+
+
+def test_finisher_rotation_compare_is_exact_to_the_byte(hl):
+    """bra_rot_cmp_window (the BWT finisher's comparison, same code on the GPU): against a plain cyclic byte comparison of
+    exactly `depth` bytes -- windows that wrap around the block end included. Looking even one byte deeper for some pairs
+    makes 'equal' non-transitive (the bug tests/golden/fuzz_case_31337_608.json records)."""
+    import json
+    import os
+    hl.hl_rot_cmp.restype = C.c_int
+    hl.hl_rot_cmp.argtypes = [u8p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+
+    def check(T, pairs, frm, depth=64):
+        p = len(T)
+        buf = np.zeros(p + 16, dtype=np.uint8)
+        buf[:p] = T
+        buf[p:] = 0xEE  # bytes past the block must never matter
+        ptr = buf.ctypes.data_as(u8p)
+        idx = np.arange(depth)
+        for a, c in pairs:
+            wa, wc = bytes(T[(a + frm + idx) % p]), bytes(T[(c + frm + idx) % p])
+            exp = (wa > wc) - (wa < wc)
+            assert hl.hl_rot_cmp(ptr, p, a, c, frm % p, depth) == exp, (p, a, c, frm)
+
+    rng = np.random.default_rng(5)
+    for it in range(300):
+        p = int(rng.integers(70, 700))
+        # runs over a tiny alphabet: long ties that end just past the window
+        T = np.repeat(rng.integers(0, 3, 64, dtype=np.uint8), rng.integers(1, 80, 64))[:p]
+        if len(T) < p:
+            T = np.resize(T, p)
+        pairs = [(int(rng.integers(0, p)), int(rng.integers(0, p))) for _ in range(60)]
+        check(T, pairs, int(rng.integers(0, 4 * p)))
+    case = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuzz_case_31337_608.json")))
+    T = np.frombuffer(bytes.fromhex(case["data"])[case["block"]:], dtype=np.uint8)
+    members = list(range(5578, 5833))
+    check(T, [(a, c) for a in members[::3] for c in members[::5]], 4096)
+    check(T, [(5766, 5633), (5766, 5637), (5633, 5766)], 4096)
