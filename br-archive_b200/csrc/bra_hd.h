@@ -260,6 +260,95 @@ BRA_HD uint32_t bra_huf_decode_one(const bra_huf_dec_t* d, uint32_t w, uint8_t* 
     return 0;
 }
 
+// ---- move-to-front list of one thread: 256 entries as sixteen 128-bit chunks ------------------------------------------
+// Q[0..15]: entry k is byte k of the 256-byte array (little endian inside each 32-bit word). Moving an entry to
+// the front shifts everything before it up by one byte: one 128-bit load, four byte-permutes and one 128-bit
+// store per sixteen entries (the instruction count is what bounds the replay kernel on high ranks, not HBM).
+#if !defined(__CUDACC__)
+struct alignas(16) uint4  // host stand-in for the CUDA vector type
+{
+    uint32_t x, y, z, w;
+};
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+#endif
+
+// (cur << 8) | (prev >> 24): the image of one 32-bit word after the shift
+BRA_HD uint32_t bra_mtf_shift_word(uint32_t prev, uint32_t cur)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(prev, cur, 0x6543);
+#else
+    return (cur << 8) | (prev >> 24);
+#endif
+}
+BRA_HD uint32_t bra_ffs32(uint32_t z)  // 1-based index of the lowest set bit, 0 for 0
+{
+#ifdef __CUDA_ARCH__
+    return (uint32_t) __ffs((int) z);
+#else
+    return (uint32_t) __builtin_ffs((int) z);
+#endif
+}
+BRA_HD uint4 bra_mtf_shift_chunk(uint32_t prev, const uint4 v)
+{
+    return make_uint4(bra_mtf_shift_word(prev, v.x), bra_mtf_shift_word(v.x, v.y), bra_mtf_shift_word(v.y, v.z), bra_mtf_shift_word(v.z, v.w));
+}
+// the chunk that holds the moved entry at byte o: bytes <= o take the shifted image, the others stay
+BRA_HD uint4 bra_mtf_merge_chunk(const uint4 v, const uint4 n, uint32_t o)
+{
+    const uint32_t wo = o >> 2;
+    const uint32_t pm = 0xFFFFFFFFu >> ((3u - (o & 3u)) * 8u);  // bytes 0..(o&3) of the word that holds the entry
+    const uint32_t mx = wo > 0 ? 0xFFFFFFFFu : pm;
+    const uint32_t my = wo > 1 ? 0xFFFFFFFFu : (wo == 1 ? pm : 0u);
+    const uint32_t mz = wo > 2 ? 0xFFFFFFFFu : (wo == 2 ? pm : 0u);
+    const uint32_t mw = wo == 3 ? pm : 0u;
+    return make_uint4((n.x & mx) | (v.x & ~mx), (n.y & my) | (v.y & ~my), (n.z & mz) | (v.z & ~mz), (n.w & mw) | (v.w & ~mw));
+}
+// decode one rank: returns the symbol at position r and moves it to the front
+BRA_HD uint32_t bra_mtf_list_decode(uint4* Q, uint32_t r)
+{
+    const uint32_t sym = reinterpret_cast<const uint8_t*>(Q)[r];
+    if (r == 0) return sym;
+    const uint32_t nq   = r >> 4;
+    uint32_t       prev = sym << 24;  // byte entering the next word from below
+    for (uint32_t q = 0; q < nq; ++q)
+    {
+        const uint4 v = Q[q];
+        Q[q]          = bra_mtf_shift_chunk(prev, v);
+        prev          = v.w;
+    }
+    const uint4 v = Q[nq];
+    Q[nq]         = bra_mtf_merge_chunk(v, bra_mtf_shift_chunk(prev, v), r & 15u);
+    return sym;
+}
+// first zero byte of t flagged in bit 7 of that byte (higher flags may be spurious, the lowest one never is)
+BRA_HD uint32_t bra_mtf_zero_bytes(uint32_t t) { return (t - 0x01010101u) & ~t & 0x80808080u; }
+// encode one symbol: returns its position and moves it to the front (single forward pass)
+BRA_HD uint32_t bra_mtf_list_encode(uint4* Q, uint32_t x)
+{
+    const uint32_t x4   = x * 0x01010101u;
+    uint32_t       prev = x << 24;
+    for (uint32_t q = 0;; ++q)
+    {
+        const uint4    v  = Q[q];
+        const uint32_t z0 = bra_mtf_zero_bytes(v.x ^ x4), z1 = bra_mtf_zero_bytes(v.y ^ x4), z2 = bra_mtf_zero_bytes(v.z ^ x4),
+                       z3 = bra_mtf_zero_bytes(v.w ^ x4);
+        const uint4    n  = bra_mtf_shift_chunk(prev, v);
+        if ((z0 | z1 | z2 | z3) == 0)
+        {
+            Q[q] = n;
+            prev = v.w;
+            continue;
+        }
+        const uint32_t wo = z0 ? 0u : (z1 ? 1u : (z2 ? 2u : 3u));
+        const uint32_t z  = z0 ? z0 : (z1 ? z1 : (z2 ? z2 : z3));
+        const uint32_t o  = wo * 4 + ((bra_ffs32(z) - 1u) >> 3);
+        if (q == 0 && o == 0) return 0;  // already in front
+        Q[q] = bra_mtf_merge_chunk(v, n, o);
+        return q * 16 + o;
+    }
+}
+
 // ---- BWT finisher: compare two rotations of T (period p) over the `depth` bytes that start `from` bytes in ----------
 // (`from` already reduced mod p; depth a multiple of 4; T 4-byte aligned). Four bytes per step through aligned word
 // loads while neither side is about to wrap around the block end, bytes otherwise. EVERY pair is compared to exactly

@@ -61,6 +61,18 @@ int hl_huf_decode(const uint8_t* lengths, const uint8_t* data, uint32_t nbytes, 
     return 0;
 }
 
+// move-to-front over one 256-entry list held as sixteen 128-bit chunks (bra_mtf_list_encode / _decode), identity list at the start
+void hl_mtf(const uint8_t* in, uint8_t* out, uint64_t n, int decode)
+{
+    uint4 Q[16];
+    for (uint32_t q = 0; q < 16; ++q)
+    {
+        const uint32_t w0 = 0x03020100u + (q * 16) * 0x01010101u;
+        Q[q]              = make_uint4(w0, w0 + 0x04040404u, w0 + 0x08080808u, w0 + 0x0C0C0C0Cu);
+    }
+    for (uint64_t i = 0; i < n; ++i) out[i] = (uint8_t) (decode ? bra_mtf_list_decode(Q, in[i]) : bra_mtf_list_encode(Q, in[i]));
+}
+
 // BWT finisher comparison (bra_rot_cmp_window); T must be 4-byte aligned and readable up to p rounded up to 4
 int hl_rot_cmp(const uint8_t* T, uint32_t p, uint32_t a, uint32_t c, uint32_t from, uint32_t depth) { return bra_rot_cmp_window(T, p, a, c, from, depth); }
 

@@ -16,6 +16,7 @@
 // steps on uniform random ranks. Traffic: read n + write n (+ 256 B of state per 4 KiB segment, twice).
 // Issue bound.
 #include "bra_common.cuh"
+#include "bra_hd.h"
 #include "bra_kernels.h"
 
 namespace bra {
@@ -26,75 +27,11 @@ namespace bra {
 #define MTF_LIST_V4 17       // 16 sixteen-byte words of list + 1 pad: odd lane stride -> lanes at the same depth use distinct bank groups
 
 // ---- per-lane list in shared memory -----------------------------------------------------------------
-// Q[0..15]: entry k is byte k of the 256-byte array (little endian inside each 32-bit word). Moving an entry to
-// the front shifts everything before it up by one byte: one 128-bit load, four byte-permutes and one 128-bit
-// store per sixteen entries (the instruction count is what bounds this kernel on high ranks, not HBM).
-
-// (cur << 8) | (prev >> 24): the image of one 32-bit word after the shift
-__device__ __forceinline__ uint32_t mtf_shift_word(uint32_t prev, uint32_t cur) { return __byte_perm(prev, cur, 0x6543); }
-
-__device__ __forceinline__ uint4 mtf_shift_chunk(uint32_t prev, const uint4 v)
-{
-    return make_uint4(mtf_shift_word(prev, v.x), mtf_shift_word(v.x, v.y), mtf_shift_word(v.y, v.z), mtf_shift_word(v.z, v.w));
-}
-
-// the chunk that holds the moved entry at byte o: bytes <= o take the shifted image, the others stay
-__device__ __forceinline__ uint4 mtf_merge_chunk(const uint4 v, const uint4 n, uint32_t o)
-{
-    const uint32_t wo = o >> 2;
-    const uint32_t pm = 0xFFFFFFFFu >> ((3u - (o & 3u)) * 8u);  // bytes 0..(o&3) of the word that holds the entry
-    const uint32_t mx = wo > 0 ? 0xFFFFFFFFu : pm;
-    const uint32_t my = wo > 1 ? 0xFFFFFFFFu : (wo == 1 ? pm : 0u);
-    const uint32_t mz = wo > 2 ? 0xFFFFFFFFu : (wo == 2 ? pm : 0u);
-    const uint32_t mw = wo == 3 ? pm : 0u;
-    return make_uint4((n.x & mx) | (v.x & ~mx), (n.y & my) | (v.y & ~my), (n.z & mz) | (v.z & ~mz), (n.w & mw) | (v.w & ~mw));
-}
-
-// decode one rank: returns the symbol at position r and moves it to the front
-__device__ __forceinline__ uint32_t lane_mtf_decode(uint4* Q, uint32_t r)
-{
-    const uint32_t sym = reinterpret_cast<const uint8_t*>(Q)[r];
-    if (r == 0) return sym;
-    const uint32_t nq   = r >> 4;
-    uint32_t       prev = sym << 24;  // byte entering the next word from below
-    for (uint32_t q = 0; q < nq; ++q)
-    {
-        const uint4 v = Q[q];
-        Q[q]          = mtf_shift_chunk(prev, v);
-        prev          = v.w;
-    }
-    const uint4 v = Q[nq];
-    Q[nq]         = mtf_merge_chunk(v, mtf_shift_chunk(prev, v), r & 15u);
-    return sym;
-}
-
-// first zero byte of t flagged in bit 7 of that byte (higher flags may be spurious, the lowest one never is)
-__device__ __forceinline__ uint32_t mtf_zero_bytes(uint32_t t) { return (t - 0x01010101u) & ~t & 0x80808080u; }
-
-// encode one symbol: returns its position and moves it to the front (single forward pass)
-__device__ __forceinline__ uint32_t lane_mtf_encode(uint4* Q, uint32_t x)
-{
-    const uint32_t x4   = x * 0x01010101u;
-    uint32_t       prev = x << 24;
-    for (uint32_t q = 0;; ++q)
-    {
-        const uint4    v  = Q[q];
-        const uint32_t z0 = mtf_zero_bytes(v.x ^ x4), z1 = mtf_zero_bytes(v.y ^ x4), z2 = mtf_zero_bytes(v.z ^ x4), z3 = mtf_zero_bytes(v.w ^ x4);
-        const uint4    n  = mtf_shift_chunk(prev, v);
-        if ((z0 | z1 | z2 | z3) == 0)
-        {
-            Q[q] = n;
-            prev = v.w;
-            continue;
-        }
-        const uint32_t wo = z0 ? 0u : (z1 ? 1u : (z2 ? 2u : 3u));
-        const uint32_t z  = z0 ? z0 : (z1 ? z1 : (z2 ? z2 : z3));
-        const uint32_t o  = wo * 4 + ((uint32_t) (__ffs((int) z) - 1) >> 3);
-        if (q == 0 && o == 0) return 0;  // already in front
-        Q[q] = mtf_merge_chunk(v, n, o);
-        return q * 16 + o;
-    }
-}
+// The list operations (bra_mtf_list_decode / bra_mtf_list_encode: find, shift by one byte, insert at the front,
+// sixteen entries per 128-bit access) live in bra_hd.h so that the CPU suite runs the very same code against a
+// naive move-to-front.
+__device__ __forceinline__ uint32_t lane_mtf_decode(uint4* Q, uint32_t r) { return bra_mtf_list_decode(Q, r); }
+__device__ __forceinline__ uint32_t lane_mtf_encode(uint4* Q, uint32_t x) { return bra_mtf_list_encode(Q, x); }
 
 // One segment per lane. MODE 0: encode (symbols -> ranks) from the segment's entry list.
 // MODE 2: decode from the IDENTITY list: the output is, per rank, the entry-list POSITION of the decoded

@@ -160,3 +160,27 @@ def test_finisher_rotation_compare_is_exact_to_the_byte(hl):
     members = list(range(5578, 5833))
     check(T, [(a, c) for a in members[::3] for c in members[::5]], 4096)
     check(T, [(5766, 5633), (5766, 5637), (5633, 5766)], 4096)
+
+
+def test_mtf_list_operations_match_the_oracle(hl, oracle):
+    """bra_mtf_list_encode / bra_mtf_list_decode (the per-thread list the GPU replay kernel runs: sixteen entries per
+    128-bit chunk, shift by byte permutes) against the oracle's move-to-front -- every rank, runs, front hits."""
+    hl.hl_mtf.restype = None
+    hl.hl_mtf.argtypes = [u8p, u8p, C.c_uint64, C.c_int]
+
+    def run(data, decode):
+        src = np.frombuffer(data, dtype=np.uint8).copy()
+        dst = np.zeros(len(src), dtype=np.uint8)
+        hl.hl_mtf(src.ctypes.data_as(u8p), dst.ctypes.data_as(u8p), len(src), decode)
+        return dst.tobytes()
+
+    rng = np.random.default_rng(11)
+    cases = [rng.integers(0, 256, 20000, dtype=np.uint8).tobytes(),                      # uniform ranks, deep shifts
+             np.repeat(rng.integers(0, 256, 500, dtype=np.uint8), rng.integers(1, 40, 500)).tobytes(),  # runs: rank 0
+             rng.integers(0, 4, 5000, dtype=np.uint8).tobytes(),                         # small alphabet: ranks 0..3
+             bytes(range(255, -1, -1)) * 8,                                              # always the last entry (rank 255)
+             bytes([15, 16, 17, 31, 32, 0, 255, 254, 16, 15] * 50)]                      # chunk borders
+    for data in cases:
+        enc = run(data, 0)
+        assert enc == oracle.mtf_encode(data)
+        assert run(enc, 1) == data == oracle.mtf_decode(enc)
