@@ -40,8 +40,8 @@ REFERENCE_API = [
 BATCH_API = [
     "bra_b200_device_count", "bra_b200_ctx_create", "bra_b200_ctx_destroy", "bra_b200_block_size", "bra_b200_max_batch",
     "bra_b200_payload_stride", "bra_b200_workspace_bytes", "bra_b200_last_stats", "bra_b200_encode_device", "bra_b200_decode_device",
-    "bra_b200_encode_bound", "bra_b200_encode_host", "bra_b200_decode_host", "bra_b200_list_host", "bra_b200_host_alloc", "bra_b200_host_free", "bra_b200_gen_random", "bra_b200_gen_text",
-    "bra_b200_gen_periodic", "bra_b200_prof_enable", "bra_b200_prof_reset", "bra_b200_prof_count", "bra_b200_prof_read",
+    "bra_b200_encode_bound", "bra_b200_encode_host", "bra_b200_decode_host", "bra_b200_list_host", "bra_b200_host_alloc", "bra_b200_host_free",
+    "bra_b200_prof_enable", "bra_b200_prof_reset", "bra_b200_prof_count", "bra_b200_prof_read",
 ]
 
 
@@ -90,9 +90,6 @@ def lib() -> C.CDLL:
     L.bra_b200_decode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), u32p]
     L.bra_b200_list_host.restype = C.c_int
     L.bra_b200_list_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
-    L.bra_b200_gen_random.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
-    L.bra_b200_gen_text.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_char_p), C.c_uint32]
-    L.bra_b200_gen_periodic.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]
     L.bra_b200_prof_enable.argtypes = [C.c_int]
     L.bra_b200_prof_count.restype = C.c_int
     L.bra_b200_prof_read.restype = C.c_int
@@ -117,32 +114,6 @@ def prof_read():
         name, n, ms = C.c_char_p(), C.c_uint64(0), C.c_double(0.0)
         L.bra_b200_prof_read(i, C.byref(name), C.byref(n), C.byref(ms))
         out[name.value.decode()] = (int(n.value), float(ms.value))
-    return out
-
-
-# ---------------------------------------------------------------------------------------------
-# synthetic workloads; numpy arrays in host memory
-# ---------------------------------------------------------------------------------------------
-def gen_random(n: int, seed: int = 2):
-    import numpy as np
-    out = np.empty(n, dtype=np.uint8)
-    lib().bra_b200_gen_random(out.ctypes.data, n, seed)
-    return out
-
-
-def gen_text(n: int, vocab, seed: int = 1):
-    import numpy as np
-    out = np.empty(n, dtype=np.uint8)
-    arr = (C.c_char_p * len(vocab))(*[v.encode("latin-1") for v in vocab])
-    lib().bra_b200_gen_text(out.ctypes.data, n, seed, arr, len(vocab))
-    return out
-
-
-def gen_periodic(n: int, pattern: bytes):
-    import numpy as np
-    out = np.empty(n, dtype=np.uint8)
-    pat = np.frombuffer(pattern, dtype=np.uint8)
-    lib().bra_b200_gen_periodic(out.ctypes.data, n, pat.ctypes.data, len(pattern))
     return out
 
 

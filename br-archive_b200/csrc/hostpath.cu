@@ -478,52 +478,3 @@ extern "C" int bra_b200_list_host(bra_b200_ctx_t* c, const uint8_t* in, uint64_t
 {
     return decode_host_impl(c, in, in_size, nullptr, 0, plain_size, nullptr, true);
 }
-
-// ---- synthetic workloads ------------------------------------------------------
-static inline uint64_t splitmix64(uint64_t& s)
-{
-    uint64_t z = (s += 0x9E3779B97F4A7C15ull);
-    z          = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z          = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-
-extern "C" void bra_b200_gen_random(uint8_t* out, uint64_t n, uint64_t seed)
-{
-    uint64_t s = seed, i = 0;
-    for (; i + 8 <= n; i += 8)
-    {
-        const uint64_t v = splitmix64(s);
-        memcpy(out + i, &v, 8);  // little-endian bytes of successive outputs
-    }
-    if (i < n)
-    {
-        const uint64_t v = splitmix64(s);
-        memcpy(out + i, &v, n - i);
-    }
-}
-
-extern "C" void bra_b200_gen_text(uint8_t* out, uint64_t n, uint64_t seed, const char* const* vocab, uint32_t nvocab)
-{
-    uint64_t s = seed, i = 0;
-    if (nvocab == 0) return;
-    std::vector<uint32_t> wl(nvocab);
-    for (uint32_t k = 0; k < nvocab; ++k) wl[k] = (uint32_t) strlen(vocab[k]);
-    bool first = true;
-    while (i < n)
-    {
-        if (!first) out[i++] = ' ';
-        first = false;
-        if (i >= n) break;
-        const uint32_t k = (uint32_t) (splitmix64(s) % nvocab);
-        const uint64_t m = std::min<uint64_t>(wl[k], n - i);
-        memcpy(out + i, vocab[k], m);
-        i += m;
-    }
-}
-
-extern "C" void bra_b200_gen_periodic(uint8_t* out, uint64_t n, const uint8_t* pattern, uint32_t plen)
-{
-    if (plen == 0) return;
-    for (uint64_t i = 0; i < n; i += plen) memcpy(out + i, pattern, (size_t) std::min<uint64_t>(plen, n - i));
-}

@@ -99,11 +99,6 @@ void bra_b200_prof_reset(void);
 int  bra_b200_prof_count(void);
 int  bra_b200_prof_read(int id, const char** name, uint64_t* launches, double* ms);
 
-/* ---- deterministic synthetic workloads; host memory -------------------- */
-void bra_b200_gen_random(uint8_t* out, uint64_t n, uint64_t seed);                                         /* C3: splitmix64 bytes */
-void bra_b200_gen_text(uint8_t* out, uint64_t n, uint64_t seed, const char* const* vocab, uint32_t nvocab); /* C2: random words joined by ' ' */
-void bra_b200_gen_periodic(uint8_t* out, uint64_t n, const uint8_t* pattern, uint32_t plen);              /* C4a/C4b */
-
 #ifdef __cplusplus
 }
 #endif

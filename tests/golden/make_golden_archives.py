@@ -17,16 +17,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 import bra_pkg  # noqa: E402
+import bra_workloads as wl  # noqa: E402
 
 
 def inputs(pkg, golden):
     vocab = golden["vocab"]
     return {
         "lorem.txt": bytes.fromhex(golden["blocks"]["lorem_txt"]["in"]),                 # 1 chunk (reference test_bra.cpp:353-398)
-        "text700k.txt": pkg.gen_text(700_000, vocab, 21).tobytes(),                      # 3 chunks of 256 KiB, ragged tail
+        "text700k.txt": wl.gen_text(700_000, vocab, 21).tobytes(),                      # 3 chunks of 256 KiB, ragged tail
         # text with an incompressible stretch inside one chunk (long runs are avoided on purpose: the reference's
         # O(n^2 log n) rotation sort needs hours on them, reference src/encoders/bra_bwt.h:27-29)
-        "mixed600k.bin": pkg.gen_text(400_000, vocab, 22).tobytes() + pkg.gen_random(50_000, 23).tobytes() + pkg.gen_text(150_000, vocab, 24).tobytes(),
+        "mixed600k.bin": wl.gen_text(400_000, vocab, 22).tobytes() + wl.gen_random(50_000, 23).tobytes() + wl.gen_text(150_000, vocab, 24).tobytes(),
     }
 
 

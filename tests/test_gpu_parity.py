@@ -10,6 +10,8 @@ import random
 import numpy as np
 import pytest
 
+import bra_workloads as wl
+
 pytestmark = pytest.mark.gpu
 
 H = bytes.fromhex
@@ -34,7 +36,7 @@ def _runs(rng, n, alphabet=3, lens=(1, 1, 1, 2, 2, 3, 4, 5, 126, 127, 128, 129, 
 
 
 def _text(pkg, vocab, n, seed=1):
-    return pkg.gen_text(n, vocab, seed).tobytes()
+    return wl.gen_text(n, vocab, seed).tobytes()
 
 
 # ------------------------------------------------------------------------------------------ CRC32C
@@ -288,7 +290,7 @@ def test_batched_small_blocks_vs_oracle(pkg, oracle, vocab):
 
 def test_batched_native_256k_blocks(pkg, oracle, vocab):
     block = 256 * 1024  # the reference's BRA_MAX_CHUNK_SIZE
-    data = _text(pkg, vocab, 3 * block + 12345) + pkg.gen_random(block, 2).tobytes()
+    data = _text(pkg, vocab, 3 * block + 12345) + wl.gen_random(block, 2).tobytes()
     _check_batch(pkg, oracle, data, block, max_batch=8)
 
 
@@ -296,7 +298,7 @@ def test_batched_1mib_text_and_random(pkg, oracle, vocab):
     """BASELINE configs 2 and 3 at full block size: a few blocks compared bit for bit with the oracle,
     all blocks round-tripped."""
     block = 1 << 20
-    data = _text(pkg, vocab, 6 * block) + pkg.gen_random(2 * block, 2).tobytes()
+    data = _text(pkg, vocab, 6 * block) + wl.gen_random(2 * block, 2).tobytes()
     st = _check_batch(pkg, oracle, data, block, max_batch=8, full_compare_blocks=[0, 5, 6])
     assert st["bwt_rounds"] >= 1
 

@@ -8,6 +8,8 @@ import sys
 import numpy as np
 import torch.multiprocessing as mp
 
+import bra_workloads as wl
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -44,7 +46,7 @@ def _worker(rank, world, port, block, data, result_q):
 
 def test_two_ranks_shard_and_fold(pkg, oracle, vocab):
     block = 4096
-    data = pkg.gen_text(9 * block + 123, vocab, 7).tobytes()
+    data = wl.gen_text(9 * block + 123, vocab, 7).tobytes()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29500 + os.getpid() % 2000

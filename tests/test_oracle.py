@@ -10,6 +10,8 @@ import random
 import numpy as np
 import pytest
 
+import bra_workloads as wl
+
 from oracle_lib import have_ref, load_ref
 
 H = bytes.fromhex
@@ -131,3 +133,27 @@ def test_fast_bwt_matches_naive_on_larger_inputs(oracle):
     for n in (4096, 20000):
         d = rng.integers(0, 4, n, dtype=np.uint8).tobytes()
         assert oracle.bwt_encode(d) == oracle.bwt_encode(d, naive=True)
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libbra_ref.so not built (needs /root/reference)")
+def test_fast_bwt_pinned_against_compiled_reference_at_block_scale(oracle, pkg, vocab):
+    """The oracle's O(n log^2 n) BWT is what every large GPU comparison leans on (the reference's own rotation sort,
+    bra_bwt.c:73-108, is O(n^2 log n) on repeats). Pin it against the compiled reference on the BASELINE shapes at the
+    largest sizes the reference finishes in seconds: 64 KiB of text and random bytes, 16 KiB of period-16 data (C4a:
+    n/16-way ties, primary 0) and of a 251-byte pattern repeated (C4b: every rotation distinct, LCP ~ n), plus the
+    whole chain on top of it."""
+    ref = load_ref()
+    rnd251 = wl.gen_random(251, 4).tobytes()
+    cases = {
+        "text64k": wl.gen_text(65536, vocab, 3).tobytes(),
+        "random64k": wl.gen_random(65536, 5).tobytes(),
+        "period16_16k": b"0123456789abcdef" * 1024,
+        "repeat251_16k": (rnd251 * 70)[:16384],
+        "repeat251_ragged": (rnd251 * 30)[:7001],
+        "runs24k": (b"a" * 300 + b"b" * 129 + b"ab" * 64) * 44,
+    }
+    for name, d in cases.items():
+        exp = ref.bwt_encode2(d)
+        assert oracle.bwt_encode(d) == exp, name
+        assert oracle.encode_block(d) == ref.encode_block(d), name
+    assert ref.bwt_encode2(cases["period16_16k"])[1] == 0
