@@ -32,17 +32,11 @@ def load_vocab():
         return json.load(f)["vocab"]
 
 
-def make_workload(pkg, kind, nbytes, seed):
-    """C2 text-like, C3 uniform random, C4a exactly periodic."""
-    if kind == "text":
-        return pkg.gen_text(nbytes, load_vocab(), seed)
-    if kind == "random":
-        return pkg.gen_random(nbytes, seed + 1)
-    if kind == "periodic":
-        return pkg.gen_periodic(nbytes, b"0123456789abcdef")
-    if kind == "repeat251":
-        return pkg.gen_periodic(nbytes, pkg.gen_random(251, 4).tobytes())  # C4b: long repeats, period does not divide the block
-    raise SystemExit(f"unknown workload {kind}")
+def make_workload(kind, nbytes, seed):
+    """C2 text-like, C3 uniform random, C4a exactly periodic, C4b long repeats
+    (tools/libbra_gen.so through bra_workloads.py: measurement tooling, not the product library)."""
+    import bra_workloads
+    return bra_workloads.make(kind, nbytes, seed, load_vocab() if kind == "text" else None)
 
 
 def workload_name(kind, nbytes, block):
@@ -100,9 +94,7 @@ def cpu_reference_run(kind, block, nblocks, seed, steps=1, warmup=0):
     reference chunks.c:214-238 / :362-397. Returns dict(value, enc_gbs, dec_gbs, cores, kind, sample)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from concurrent.futures import ThreadPoolExecutor
-    import bra_pkg
     import oracle_lib
-    pkg = bra_pkg.load()
     cores = os.cpu_count() or 1
     if oracle_lib.have_ref():
         impl, kind_name = oracle_lib.load_ref(), "reference"
@@ -112,7 +104,7 @@ def cpu_reference_run(kind, block, nblocks, seed, steps=1, warmup=0):
         impl, kind_name = oracle_lib.Oracle(), "port"
         enc = impl.encode_block
         dec = lambda h, p, n: impl.decode_block(h, p, n)
-    data = make_workload(pkg, kind, nblocks * block, seed).tobytes()
+    data = make_workload(kind, nblocks * block, seed).tobytes()
     blocks = [data[i * block:(i + 1) * block] for i in range(nblocks)]
     t_enc, t_dec = [], []
     with ThreadPoolExecutor(max_workers=cores) as ex:
@@ -199,7 +191,7 @@ def main():
             dist.barrier()
 
     # ---- workload: generated on the host (pinned), resident in HBM before the timed region -------------
-    host = torch.from_numpy(make_workload(pkg, args.workload, nbytes, seed=1 + rank)).pin_memory()
+    host = torch.from_numpy(make_workload(args.workload, nbytes, seed=1 + rank)).pin_memory()
     d_in = host.cuda(non_blocking=True)
     nblk = (nbytes + block - 1) // block
     ctx = pkg.Context(local_rank, block, min(args.batch, nblk))

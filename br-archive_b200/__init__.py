@@ -40,7 +40,7 @@ REFERENCE_API = [
 BATCH_API = [
     "bra_b200_device_count", "bra_b200_ctx_create", "bra_b200_ctx_destroy", "bra_b200_block_size", "bra_b200_max_batch",
     "bra_b200_payload_stride", "bra_b200_workspace_bytes", "bra_b200_last_stats", "bra_b200_encode_device", "bra_b200_decode_device",
-    "bra_b200_encode_bound", "bra_b200_encode_host", "bra_b200_decode_host", "bra_b200_list_host", "bra_b200_host_alloc", "bra_b200_host_free",
+    "bra_b200_encode_bound", "bra_b200_encode_host", "bra_b200_decode_host", "bra_b200_list_host", "bra_b200_host_alloc", "bra_b200_host_free", "bra_b200_crc32c_submit", "bra_b200_crc32c_finish",
     "bra_b200_prof_enable", "bra_b200_prof_reset", "bra_b200_prof_count", "bra_b200_prof_read",
 ]
 

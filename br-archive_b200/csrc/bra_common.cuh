@@ -36,6 +36,32 @@ void bra_b200_log_error(const char* fmt, ...);
 
 static inline uint32_t bra_div_up(uint64_t a, uint64_t b) { return (uint32_t) ((a + b - 1) / b); }
 
+// Makes `dev` the current device for the lifetime of the guard and restores the caller's device afterwards: library
+// entry points must not leave a different current device behind in the calling thread.
+struct BraDeviceGuard
+{
+    int  prev = -1;
+    bool ok   = false;
+    explicit BraDeviceGuard(int dev)
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess) return;
+        if (cur == dev)
+        {
+            ok = true;
+            return;
+        }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+        if (ok) prev = cur;
+    }
+    ~BraDeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    BraDeviceGuard(const BraDeviceGuard&)            = delete;
+    BraDeviceGuard& operator=(const BraDeviceGuard&) = delete;
+};
+
 #ifdef __CUDACC__
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }

@@ -30,6 +30,7 @@ bool       g_ready = false;
 uint8_t*   g_buf   = nullptr;  // device scratch, grown on demand
 uint64_t   g_cap   = 0;
 cudaStream_t g_st  = nullptr;
+int        g_dev   = 0;  // the device that was current at the first call: the per-stage API stays on it (scratch, stream, CRC tables)
 
 bool stage_init()
 {
@@ -40,11 +41,18 @@ bool stage_init()
         bra_b200_log_error("bra_b200: no CUDA device available and there is no CPU fallback");
         return false;
     }
+    BRA_CUDA_TRY(cudaGetDevice(&g_dev));
     if (!crc_init_tables()) return false;
     BRA_CUDA_TRY(cudaStreamCreateWithFlags(&g_st, cudaStreamNonBlocking));
     g_ready = true;
     return true;
 }
+
+// every per-stage entry: library initialised, and the stage device current until the entry returns
+#define STAGE_ENTER(fail)            \
+    if (!stage_init()) return fail;  \
+    BraDeviceGuard _dg(g_dev);       \
+    if (!_dg.ok) return fail
 
 struct Bump
 {
@@ -99,7 +107,11 @@ extern "C" __attribute__((weak)) bool bra_init(void)
 extern "C" __attribute__((weak)) bool bra_quit(void)
 {
     std::lock_guard<std::mutex> lk(g_mu);
-    if (g_buf) cudaFree(g_buf);
+    if (g_buf)
+    {
+        BraDeviceGuard dg(g_dev);
+        cudaFree(g_buf);
+    }
     g_buf = nullptr;
     g_cap = 0;
     return true;
@@ -113,7 +125,7 @@ static uint32_t crc_device(const void* data, uint64_t length, uint32_t prev)
 {
     if (length == 0 || data == nullptr) return prev;  // reference: empty/NULL input leaves the CRC unchanged (test_bra_crc32c.cpp:38-43)
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!stage_init()) return 0;
+    STAGE_ENTER(0);
     // inputs above 2^32-1 bytes are folded piecewise (kernel lengths are 32-bit)
     const uint8_t* p   = static_cast<const uint8_t*>(data);
     uint32_t       crc = prev;
@@ -154,7 +166,7 @@ extern "C" bool bra_bwt_encode2(const uint8_t* buf, const bra_bwt_index_t n, bra
         return false;
     }
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!stage_init()) return false;
+    STAGE_ENTER(false);
     const uint64_t S     = pad16(n);
     const uint64_t tiles = bra_div_up(S, 4096);
     Bump           B;
@@ -207,7 +219,7 @@ static bool bwt_decode_impl(const uint8_t* buf, uint32_t n, uint32_t pi, uint32_
         return false;
     }
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!stage_init()) return false;
+    STAGE_ENTER(false);
     const uint64_t S = pad16(n), km = ibwt_kmax(n);
     Bump           B;
     const uint64_t o_in = B.take<uint8_t>(S), o_out = B.take<uint8_t>(S), o_W = B.take<uint32_t>(S);
@@ -263,7 +275,7 @@ static bool mtf_impl(const uint8_t* buf, size_t n, uint8_t* out_buf, bool encode
         return false;
     }
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!stage_init()) return false;
+    STAGE_ENTER(false);
     const uint32_t n32 = (uint32_t) n;
     const uint64_t S = pad16(n), segs = mtf_segments(n32);
     Bump           B;
@@ -319,7 +331,7 @@ extern "C" bool bra_rle_encode(const uint8_t* buf, const size_t n, uint8_t** out
         return false;
     }
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!stage_init()) return false;
+    STAGE_ENTER(false);
     const uint32_t n32 = (uint32_t) n;
     const uint64_t S = pad16(n), RS = pad16(n + n / 128 + 64), tiles = rle_enc_tiles(n32);
     Bump           B;
@@ -358,13 +370,15 @@ static bool rle_decode_impl(const uint8_t* buf, size_t n, bool size_only, uint8_
     *out_size = 0;
     if (out_buf) *out_buf = nullptr;
     if (!buf || n == 0) return false;
-    if (n > 0x20000000u)
+    // tile output counts are summed in 32 bits and a run token expands 64x: 64 MiB of input can never wrap them
+    // (the format's chunks are at most 16 MiB + 1/128)
+    if (n > 0x03FFFFFFu)
     {
         bra_b200_log_error("bra_rle_decode: input of %zu bytes is above this implementation's limit", n);
         return false;
     }
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!stage_init()) return false;
+    STAGE_ENTER(false);
     const uint32_t r32 = (uint32_t) n;
     const uint64_t RS = pad16(n + 16), tiles = rle_dec_tiles(r32);
     Bump           B;
@@ -444,7 +458,7 @@ extern "C" bra_huffman_chunk_t* bra_huffman_encode(const uint8_t* buf, const uin
         return nullptr;
     }
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!stage_init()) return nullptr;
+    STAGE_ENTER(nullptr);
     const uint64_t RS = pad16(n), tiles = huf_enc_tiles(n);
     const uint64_t PS = pad16((uint64_t) n * 34 / 8 + 64);  // payload bound for ANY length assignment the tree can produce
     Bump           B;
@@ -489,13 +503,13 @@ extern "C" uint8_t* bra_huffman_decode(const bra_huffman_t* meta, const uint8_t*
         }
         return static_cast<uint8_t*>(malloc(1));
     }
-    if (r > 0x20000000u || c > 0x20000000u)
+    if (r > 0x20000000u || c >= 0x20000000u)  // bit offsets (c * 8) are 32-bit
     {
         bra_b200_log_error("bra_huffman_decode: sizes above this implementation's limit (%u, %u)", r, c);
         return nullptr;
     }
     std::lock_guard<std::mutex> lk(g_mu);
-    if (!stage_init()) return nullptr;
+    STAGE_ENTER(nullptr);
     const uint64_t PS = pad16((uint64_t) c + 64), RS = pad16((uint64_t) r + 16), seqs = huf_dec_seqs(c);
     Bump           B;
     const uint64_t o_pay = B.take<uint8_t>(PS), o_hdr = B.take<uint8_t>(272), o_out = B.take<uint8_t>(RS), o_tab = B.take<bra_huf_dec_t>(1);

@@ -15,41 +15,53 @@
 #include "bra_hd.h"
 #include "bra_kernels.h"
 
+#include <mutex>
+
 namespace bra {
 
 __device__ uint32_t       g_crc_tab[4][256];   // slicing-by-4 tables
 __device__ uint32_t       g_crc_seg_pow[256];  // x^(8*64*j) mod P
 __device__ bra_gf_pow_t   g_gf_pow;
 static bra_gf_pow_t       h_gf_pow;
-static bool               h_crc_ready = false;
+static std::once_flag     h_crc_once;
 
 const bra_gf_pow_t* crc_host_pow()
 {
-    if (!h_crc_ready)
-    {
-        bra_gf_init_pow(&h_gf_pow);
-        h_crc_ready = true;
-    }
+    std::call_once(h_crc_once, [] { bra_gf_init_pow(&h_gf_pow); });  // reached from any thread (bra_crc32c_combine, the host paths)
     return &h_gf_pow;
 }
 
+// Uploads the tables to the CURRENT device once (module globals exist per device). Thread-safe: contexts on several
+// GPUs may be created from several host threads.
 bool crc_init_tables()
 {
-    static uint32_t tab[4][256];
-    static uint32_t seg[256];
-    for (uint32_t b = 0; b < 256; ++b)
-    {
-        uint32_t r = b;
-        for (int k = 0; k < 8; ++k) r = (r & 1u) ? (r >> 1) ^ BRA_CRC_POLY : (r >> 1);
-        tab[0][b] = r;
-    }
-    for (int k = 1; k < 4; ++k)
-        for (uint32_t b = 0; b < 256; ++b) tab[k][b] = tab[0][tab[k - 1][b] & 0xFFu] ^ (tab[k - 1][b] >> 8);
+    static std::mutex mu;
+    static bool       ready[64] = {false};
+    static uint32_t   tab[4][256];
+    static uint32_t   seg[256];
+    static bool       host_ready = false;
+    int               dev = 0;
+    BRA_CUDA_TRY(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev >= 0 && dev < 64 && ready[dev]) return true;
     const bra_gf_pow_t* pw = crc_host_pow();
-    for (uint32_t j = 0; j < 256; ++j) seg[j] = bra_gf_xpow8(pw, 64ull * j);
+    if (!host_ready)
+    {
+        for (uint32_t b = 0; b < 256; ++b)
+        {
+            uint32_t r = b;
+            for (int k = 0; k < 8; ++k) r = (r & 1u) ? (r >> 1) ^ BRA_CRC_POLY : (r >> 1);
+            tab[0][b] = r;
+        }
+        for (int k = 1; k < 4; ++k)
+            for (uint32_t b = 0; b < 256; ++b) tab[k][b] = tab[0][tab[k - 1][b] & 0xFFu] ^ (tab[k - 1][b] >> 8);
+        for (uint32_t j = 0; j < 256; ++j) seg[j] = bra_gf_xpow8(pw, 64ull * j);
+        host_ready = true;
+    }
     BRA_CUDA_TRY(cudaMemcpyToSymbol(g_crc_tab, tab, sizeof(tab)));
     BRA_CUDA_TRY(cudaMemcpyToSymbol(g_crc_seg_pow, seg, sizeof(seg)));
     BRA_CUDA_TRY(cudaMemcpyToSymbol(g_gf_pow, pw, sizeof(bra_gf_pow_t)));
+    if (dev >= 0 && dev < 64) ready[dev] = true;
     return true;
 }
 

@@ -47,23 +47,46 @@ static double trace_ms()
 namespace {
 
 // out offsets (exclusive scan of 267 + clen) for up to 32768 blocks: one CTA
+// (64-bit throughout: 1024 chunks of 4 MiB or more of incompressible data exceed 2^32 stream bytes)
 __global__ void __launch_bounds__(1024) stream_offsets_kernel(const uint8_t* __restrict__ hdr, uint32_t nblk, uint64_t* __restrict__ off)
 {
-    __shared__ uint32_t red[34];
-    uint64_t            carry = 0;
+    __shared__ unsigned long long red[33];
+    unsigned long long            carry = 0;
+    const uint32_t                w = warp_id(), l = lane_id();
     for (uint32_t base = 0; base < nblk; base += 1024)
     {
-        const uint32_t b = base + threadIdx.x;
-        uint32_t       v = 0;
+        const uint32_t     b = base + threadIdx.x;
+        unsigned long long v = 0;
         if (b < nblk)
         {
             const uint8_t* h = hdr + (uint64_t) b * 268 + 264;
-            v = 267u + ((uint32_t) h[0] | ((uint32_t) h[1] << 8) | ((uint32_t) h[2] << 16) | ((uint32_t) h[3] << 24));
+            v = 267ull + ((uint32_t) h[0] | ((uint32_t) h[1] << 8) | ((uint32_t) h[2] << 16) | ((uint32_t) h[3] << 24));
         }
-        uint32_t       tot;
-        const uint32_t ex = block_excl_add(v, red, &tot);
-        if (b < nblk) off[b] = carry + ex;
-        carry += tot;
+        unsigned long long inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1)
+        {
+            const unsigned long long t = __shfl_up_sync(BRA_FULL, inc, d);
+            if (l >= (uint32_t) d) inc += t;
+        }
+        if (l == 31) red[w] = inc;
+        __syncthreads();
+        if (w == 0)
+        {
+            const unsigned long long x = red[l];
+            unsigned long long       s = x;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1)
+            {
+                const unsigned long long t = __shfl_up_sync(BRA_FULL, s, d);
+                if (l >= (uint32_t) d) s += t;
+            }
+            red[l] = s - x;
+            if (l == 31) red[32] = s;
+        }
+        __syncthreads();
+        if (b < nblk) off[b] = carry + red[w] + inc - v;
+        carry += red[32];
         __syncthreads();
     }
     if (threadIdx.x == 0) off[nblk] = carry;
@@ -83,7 +106,7 @@ __global__ void __launch_bounds__(256)
         out[o + i] = i < 3 ? h[i] : (i < 267 ? h[i + 1] : p[i - 267]);
 }
 
-// scatter: inverse of the gather, plus zero slack after each payload
+// scatter: inverse of the gather (bytes past a payload are never read as data: the Huffman staging masks them)
 __global__ void __launch_bounds__(256)
     stream_scatter_kernel(const uint8_t* __restrict__ in, const uint64_t* __restrict__ off, uint8_t* __restrict__ hdr, uint8_t* __restrict__ pay,
                           uint64_t pay_stride)
@@ -145,10 +168,10 @@ extern "C" uint64_t bra_b200_encode_bound(const bra_b200_ctx_t* c, uint64_t tota
 namespace {
 struct Pipe
 {
-    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr, s_comp = nullptr;  // s_comp: the context's compute stream (not owned)
     cudaEvent_t  ev_in[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     bool         ok = false;
-    Pipe()
+    explicit Pipe(cudaStream_t comp) : s_comp(comp)
     {
         ok = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking) == cudaSuccess &&
              cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking) == cudaSuccess;
@@ -159,6 +182,11 @@ struct Pipe
     }
     ~Pipe()
     {
+        // Every return path, error paths included, leaves with no copy or kernel in flight: the transfers touch the
+        // caller's buffers and the context's staging memory, which the caller may free or reuse right after the call.
+        if (s_in) cudaStreamSynchronize(s_in);
+        if (s_comp) cudaStreamSynchronize(s_comp);
+        if (s_out) cudaStreamSynchronize(s_out);
         for (int i = 0; i < 2; ++i)
         {
             if (ev_in[i]) cudaEventDestroy(ev_in[i]);
@@ -191,7 +219,8 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
         bra_b200_log_error("bra_b200_encode_host: invalid arguments");
         return 1;
     }
-    if (cudaSetDevice(ctx_device(c)) != cudaSuccess) return 2;
+    BraDeviceGuard dg(ctx_device(c));
+    if (!dg.ok) return 2;
     const uint32_t S  = bra_b200_block_size(c);
     const uint32_t HB = stage_blocks(bra_b200_max_batch(c));
     const uint64_t PS = bra_b200_payload_stride(c);
@@ -202,7 +231,7 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
     for (uint64_t i = 0; i < nstage; ++i) first[i + 1] = first[i] + plan[i];
     cudaStream_t   st = ctx_stream(c);
     *out_size         = 0;
-    Pipe P;
+    Pipe P(st);
     if (!P.ok) return 2;
 
     // device staging: input x2 | hdr | payload | stream x2 | offsets | crcs
@@ -291,13 +320,14 @@ static int decode_host_impl(bra_b200_ctx_t* c, const uint8_t* in, uint64_t in_si
         bra_b200_log_error("bra_b200_decode_host: invalid arguments");
         return 1;
     }
-    if (cudaSetDevice(ctx_device(c)) != cudaSuccess) return 2;
+    BraDeviceGuard dg(ctx_device(c));
+    if (!dg.ok) return 2;
     const uint32_t S  = bra_b200_block_size(c);
     const uint32_t HB = stage_blocks(bra_b200_max_batch(c));
     const uint64_t PS = bra_b200_payload_stride(c);
     cudaStream_t   st = ctx_stream(c);
     *out_size         = 0;
-    Pipe P;
+    Pipe P(st);
     if (!P.ok) return 2;
 
     auto           up    = [](uint64_t v) { return (v + 255) / 256 * 256; };

@@ -10,6 +10,7 @@
 // Block b of a batch always lives at offset b*stride (or b*rle_stride, ...) of an array, so a
 // kernel addresses it from blockIdx.y alone and lengths stay in device memory between stages.
 #include "bra_common.cuh"
+#include "bra_hd.h"
 #include "bra_kernels.h"
 #include "pipeline.h"
 
@@ -150,6 +151,7 @@ struct bra_b200_ctx
     // pinned, device-visible host words for the small transfers of the control loops (mail_fetch / mail_publish):
     // [bwt: 2 + BRA_DIV_CAP + 2*max_batch][huffman: 16][block lengths: max_batch][host path: 8*max_batch + 16]
     uint32_t* h_mail = nullptr;
+    uint64_t  crc_pending = 0;  // bytes of the CRC submission in flight (bra_b200_crc32c_submit), 0 = none
 };
 
 static inline uint32_t* mail_bwt(bra_b200_ctx* c) { return c->h_mail; }
@@ -221,19 +223,11 @@ __global__ void zero_len_on_err_kernel(uint32_t* __restrict__ len, const uint32_
 }
 
 // ---- context --------------------------------------------------------------------------------------
-static bool g_tables_ready[64] = {false};
-
 extern "C" int bra_b200_device_count(void)
 {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) return -1;
     return n;
-}
-
-static bool ctx_bind(bra_b200_ctx* c)
-{
-    BRA_CUDA_TRY(cudaSetDevice(c->device));
-    return true;
 }
 
 extern "C" bra_b200_ctx_t* bra_b200_ctx_create(int device, uint32_t block_size, uint32_t max_batch)
@@ -255,12 +249,9 @@ extern "C" bra_b200_ctx_t* bra_b200_ctx_create(int device, uint32_t block_size, 
     c->max_batch  = max_batch;
     c->rle_stride = rle_stride_for(block_size);
     c->pay_stride = pay_stride_for(block_size);
-    if (cudaSetDevice(device) != cudaSuccess) { delete c; return nullptr; }
-    if (device < 64 && !g_tables_ready[device])
-    {
-        if (!crc_init_tables()) { delete c; return nullptr; }
-        g_tables_ready[device] = true;
-    }
+    BraDeviceGuard dg(device);
+    if (!dg.ok) { delete c; return nullptr; }
+    if (!crc_init_tables()) { delete c; return nullptr; }  // per device, thread-safe
     // size the arena by dry-running both carves
     Arena dry;
     EncWs ew;
@@ -292,7 +283,7 @@ extern "C" bra_b200_ctx_t* bra_b200_ctx_create(int device, uint32_t block_size, 
 extern "C" void bra_b200_ctx_destroy(bra_b200_ctx_t* c)
 {
     if (!c) return;
-    cudaSetDevice(c->device);
+    BraDeviceGuard dg(c->device);
     if (c->arena.base) cudaFree(c->arena.base);
     if (c->d_io) cudaFree(c->d_io);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -439,7 +430,8 @@ extern "C" int bra_b200_encode_device(bra_b200_ctx_t* c, const uint8_t* d_in, ui
         bra_b200_log_error("bra_b200_encode_device: invalid arguments");
         return 1;
     }
-    if (!ctx_bind(c)) return 2;
+    BraDeviceGuard dg(c->device);
+    if (!dg.ok) return 2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     c->last_rounds  = 0;
     const uint64_t launches0 = prof_total_launches();
@@ -465,7 +457,8 @@ extern "C" int bra_b200_decode_device(bra_b200_ctx_t* c, const uint8_t* d_hdr, c
         bra_b200_log_error("bra_b200_decode_device: invalid arguments");
         return 1;
     }
-    if (!ctx_bind(c)) return 2;
+    BraDeviceGuard dg(c->device);
+    if (!dg.ok) return 2;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     c->last_sweeps  = 0;
     const uint64_t launches0 = prof_total_launches();
@@ -478,6 +471,44 @@ extern "C" int bra_b200_decode_device(bra_b200_ctx_t* c, const uint8_t* d_hdr, c
     }
     if (cudaStreamSynchronize(st) != cudaSuccess) return 4;
     c->last_launches = prof_total_launches() - launches0;
+    return 0;
+}
+
+// ---- streaming CRC-32C of host memory (the STORED path, reference chunks.c:114-167) -------------------------
+extern "C" int bra_b200_crc32c_submit(bra_b200_ctx_t* c, const void* data, uint64_t len)
+{
+    if (!c || !data || len == 0 || len > (1ull << 30) || c->crc_pending)
+    {
+        bra_b200_log_error("bra_b200_crc32c_submit: invalid arguments or a submission is already in flight");
+        return 1;
+    }
+    BraDeviceGuard dg(c->device);
+    if (!dg.ok) return 2;
+    const uint64_t padded = (len + 15) / 16 * 16;
+    uint8_t*       io     = ctx_io_buffer(c, padded + 256);
+    if (!io) return 3;
+    cudaStream_t st    = c->own_stream;
+    uint32_t*    d_crc = reinterpret_cast<uint32_t*>(io + padded);
+    if (cudaMemcpyAsync(io, data, len, cudaMemcpyHostToDevice, st) != cudaSuccess) return 4;
+    if (!crc_blocks(io, padded, nullptr, (uint32_t) len, (uint32_t) len, 1, nullptr, d_crc, st)) return 5;
+    if (!mail_publish(ctx_mail_host(c), d_crc, 1, st)) return 5;
+    c->crc_pending = len;
+    return 0;
+}
+
+extern "C" int bra_b200_crc32c_finish(bra_b200_ctx_t* c, uint32_t* crc)
+{
+    if (!c || c->crc_pending == 0) return 1;
+    BraDeviceGuard dg(c->device);
+    if (!dg.ok) return 2;
+    const uint64_t len = c->crc_pending;
+    c->crc_pending     = 0;
+    if (cudaStreamSynchronize(c->own_stream) != cudaSuccess) return 4;
+    if (crc)
+    {
+        const uint32_t piece = *reinterpret_cast<volatile uint32_t*>(ctx_mail_host(c));  // crc32c(data, len, 0)
+        *crc                 = bra_crc_combine(crc_host_pow(), *crc, piece, len);        // == crc32c(data, len, *crc)
+    }
     return 0;
 }
 

@@ -22,19 +22,34 @@ struct ProfSlot
 {
     std::atomic<uint64_t> launches{0};
     double                ms = 0;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+    struct Bracket
+    {
+        cudaEvent_t a, b;
+        int         dev;
+    };
+    std::vector<Bracket> pending;
 };
 static ProfSlot   g_slots[P_COUNT];
 static bool       g_timing = false;
 static std::mutex g_prof_mu;
-static std::vector<cudaEvent_t> g_pool;
+// CUDA events belong to the device that was current when they were created: one pool per device, so that several
+// contexts on different GPUs of one process (bra_b200_pool) can be timed at once.
+#define PROF_MAX_DEV 64
+static std::vector<cudaEvent_t> g_pool[PROF_MAX_DEV];
 
-static cudaEvent_t take_event()
+static int prof_device()
 {
-    if (!g_pool.empty())
+    int d = 0;
+    cudaGetDevice(&d);
+    return (d >= 0 && d < PROF_MAX_DEV) ? d : 0;
+}
+
+static cudaEvent_t take_event(int dev)
+{
+    if (!g_pool[dev].empty())
     {
-        cudaEvent_t e = g_pool.back();
-        g_pool.pop_back();
+        cudaEvent_t e = g_pool[dev].back();
+        g_pool[dev].pop_back();
         return e;
     }
     cudaEvent_t e = nullptr;
@@ -47,16 +62,17 @@ void prof_pre(int id, cudaStream_t st)
     g_slots[id].launches.fetch_add(1, std::memory_order_relaxed);
     if (!g_timing) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    cudaEvent_t a = take_event(), b = take_event();
+    const int   dev = prof_device();
+    cudaEvent_t a = take_event(dev), b = take_event(dev);
     cudaEventRecord(a, st);
-    g_slots[id].pending.push_back({a, b});
+    g_slots[id].pending.push_back({a, b, dev});
 }
 
 void prof_post(int id, cudaStream_t st)
 {
     if (!g_timing) return;
     std::lock_guard<std::mutex> lk(g_prof_mu);
-    if (!g_slots[id].pending.empty()) cudaEventRecord(g_slots[id].pending.back().second, st);
+    if (!g_slots[id].pending.empty()) cudaEventRecord(g_slots[id].pending.back().b, st);
 }
 
 uint64_t prof_total_launches()
@@ -73,9 +89,9 @@ static void prof_drain()
         for (auto& pr : g_slots[i].pending)
         {
             float ms = 0;
-            if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) g_slots[i].ms += ms;
-            g_pool.push_back(pr.first);
-            g_pool.push_back(pr.second);
+            if (cudaEventSynchronize(pr.b) == cudaSuccess && cudaEventElapsedTime(&ms, pr.a, pr.b) == cudaSuccess) g_slots[i].ms += ms;
+            g_pool[pr.dev].push_back(pr.a);
+            g_pool[pr.dev].push_back(pr.b);
         }
         g_slots[i].pending.clear();
     }

@@ -33,15 +33,46 @@
 #include <stdlib.h>
 #include <string.h>
 
-#define B200_WINDOW_CHUNKS 1024u /* chunks handed to the GPU per call: 256 MiB of plain data at the default chunk size */
+#define B200_WINDOW_BYTES ((uint64_t) 256 << 20) /* plain data handed to the GPU per call */
 
-static bra_b200_ctx_t* g_b200_ctx = NULL;
+static bra_b200_ctx_t* g_b200_ctx   = NULL;
+static uint32_t        g_b200_chunk = 0; /* run-time chunk size; BRA_MAX_CHUNK_SIZE unless overridden */
+
+/* Chunk size: the reference fixes it at compile time (BRA_MAX_CHUNK_SIZE, lib_bra_defs.h:93). Here it is a run-time
+ * parameter of the library; BRA_B200_BLOCK_KIB=<KiB> (16 .. 16384, the 3-byte primary index bounds it) selects it
+ * for the CLI, so that the 1 MiB / 8 MiB BASELINE configurations run through `bra` / `unbra`. Archives written with
+ * a larger chunk size need the same setting to be read back (the reference reader rejects chunks above its
+ * compile-time size, chunks.c:31-48, and so does this one above its run-time size). */
+static uint32_t b200_chunk_size(void)
+{
+    if (g_b200_chunk == 0)
+    {
+        g_b200_chunk  = BRA_MAX_CHUNK_SIZE;
+        const char* e = getenv("BRA_B200_BLOCK_KIB");
+        if (e != NULL && *e != '\0')
+        {
+            char*               end = NULL;
+            const unsigned long kib = strtoul(e, &end, 10);
+            if (end != NULL && *end == '\0' && kib >= 16 && kib <= 16384)
+                g_b200_chunk = (uint32_t) (kib * 1024u);
+            else
+                bra_log_warn("BRA_B200_BLOCK_KIB=%s ignored (expected 16..16384)", e);
+        }
+    }
+    return g_b200_chunk;
+}
+
+static uint32_t b200_window_chunks(void)
+{
+    const uint64_t n = B200_WINDOW_BYTES / b200_chunk_size();
+    return (uint32_t) (n < 4 ? 4 : n);
+}
 
 static bra_b200_ctx_t* b200_ctx(void)
 {
     if (g_b200_ctx == NULL)
     {
-        g_b200_ctx = bra_b200_ctx_create(0, BRA_MAX_CHUNK_SIZE, B200_WINDOW_CHUNKS);
+        g_b200_ctx = bra_b200_ctx_create(0, b200_chunk_size(), b200_window_chunks());
         if (g_b200_ctx == NULL)
             bra_log_critical("unable to create the GPU compression context (no CPU fallback)");
     }
@@ -49,7 +80,7 @@ static bra_b200_ctx_t* b200_ctx(void)
 }
 
 /* Window buffers: page-locked (the GPU copies run at the full PCIe rate from and to them) and kept between calls,
- * like the reference's own g_buf scratch (lib_bra.c:25-45). [0] = plain side, [1] = chunk-stream side.
+ * like the reference's own g_buf scratch (lib_bra.c:25-45). [0] = plain side, [1] = chunk-stream side, [2] = STORED copies.
  * If page-locking fails they are ordinary memory: slower copies, same results. */
 typedef struct
 {
@@ -57,7 +88,7 @@ typedef struct
     uint64_t cap;
     bool     pinned;
 } b200_window_t;
-static b200_window_t g_window[2];
+static b200_window_t g_window[3]; /* [2] = the STORED path's double buffer */
 
 static uint8_t* b200_window(const int which, const uint64_t bytes)
 {
@@ -83,7 +114,8 @@ static bool chunk_header_is_valid(const uint8_t* disk_hdr) /* chunks.c:31-48 on 
     uint32_t       orig, enc;
     memcpy(&orig, disk_hdr + 3 + BRA_ALPHABET_SIZE, 4);
     memcpy(&enc, disk_hdr + 3 + BRA_ALPHABET_SIZE + 4, 4);
-    return pi < BRA_MAX_CHUNK_SIZE && enc <= BRA_MAX_CHUNK_SIZE && orig <= BRA_MAX_CHUNK_SIZE && enc != 0 && orig != 0;
+    const uint32_t cs = b200_chunk_size();
+    return pi < cs && enc <= cs && orig <= cs && enc != 0 && orig != 0;
 }
 
 /* ---- header I/O: 3-byte index + packed Huffman header (chunks.c:52-95) --------------------------------- */
@@ -141,32 +173,49 @@ bool bra_io_file_chunks_read_file(bra_io_file_t* src, const uint64_t data_size, 
     }
 }
 
-/* ---- STORED path (chunks.c:114-167): stream through a host buffer, CRC on the GPU per piece ------------------- */
+/* ---- STORED path (chunks.c:114-167): double-buffered page-locked window; the GPU computes the CRC of piece k
+ * (bra_b200_crc32c_submit: H2D copy + kernels, asynchronous) while piece k is written out and piece k+1 is read -------- */
 bool bra_io_file_chunks_copy_file(bra_io_file_t* dst, bra_io_file_t* src, const uint64_t data_size, bra_meta_entry_t* me, const bool compute_crc32)
 {
     assert_bra_io_file_t(src);
-    const size_t piece = (size_t) 64 << 20; /* large pieces: one GPU CRC call per piece instead of per 256 KiB */
-    uint8_t*     buf   = NULL;
+    const uint64_t  piece = (uint64_t) 64 << 20;
+    bra_b200_ctx_t* ctx   = NULL;
+    bool            busy  = false; /* a CRC submission is in flight */
     if (dst != NULL && (dst->f == NULL || dst->fn == NULL)) goto fail;
     if (compute_crc32 && me == NULL)
     {
         bra_log_critical("can't compute crc32: me is null");
         goto fail;
     }
-    buf = malloc(data_size < piece ? (data_size ? data_size : 1) : piece);
+    if (data_size == 0) return true;
+    if (compute_crc32 && (ctx = b200_ctx()) == NULL) goto fail;
+    const uint64_t half = data_size < piece ? data_size : piece;
+    uint8_t*       buf  = b200_window(2, 2 * half);
     if (buf == NULL) goto fail;
-    for (uint64_t i = 0; i < data_size;)
+    int k = 0;
+    for (uint64_t i = 0; i < data_size; k ^= 1)
     {
-        const size_t s = (size_t) _bra_min(piece, data_size - i);
-        if (!bra_io_file_read(src, buf, s)) goto fail;
-        if (compute_crc32) me->crc32 = bra_crc32c(buf, s, me->crc32);
-        if (dst != NULL && !bra_io_file_write(dst, buf, s)) goto fail;
+        const uint64_t s = _bra_min(piece, data_size - i);
+        uint8_t*       p = buf + (uint64_t) k * half;
+        if (!bra_io_file_read(src, p, s)) goto fail;
+        if (compute_crc32)
+        {
+            if (busy && bra_b200_crc32c_finish(ctx, &me->crc32) != 0) goto fail; /* piece k-1; its half is reused next round */
+            busy = false;
+            if (bra_b200_crc32c_submit(ctx, p, s) != 0) goto fail;
+            busy = true;
+        }
+        if (dst != NULL && !bra_io_file_write(dst, p, s)) goto fail;
         i += s;
     }
-    free(buf);
+    if (busy && bra_b200_crc32c_finish(ctx, &me->crc32) != 0)
+    {
+        busy = false;
+        goto fail;
+    }
     return true;
 fail:
-    free(buf);
+    if (busy) (void) bra_b200_crc32c_finish(ctx, NULL);
     if (dst != NULL) bra_io_file_close(dst);
     bra_io_file_close(src);
     return false;
@@ -182,7 +231,8 @@ bool bra_io_file_chunks_compress_file(bra_io_file_t* dst, bra_io_file_t* src, co
     bra_b200_ctx_t* ctx = b200_ctx();
     if (ctx == NULL) return false;
 
-    const uint64_t window = (uint64_t) B200_WINDOW_CHUNKS * BRA_MAX_CHUNK_SIZE;
+    const uint32_t chunk  = b200_chunk_size();
+    const uint64_t window = (uint64_t) b200_window_chunks() * chunk;
     uint8_t*       in     = NULL;
     uint8_t*       out    = NULL;
     uint32_t       crc32  = BRA_CRC32C_INIT;
@@ -231,8 +281,8 @@ bool bra_io_file_chunks_compress_file(bra_io_file_t* dst, bra_io_file_t* src, co
     else
     {
         if (!bra_io_file_seek(&tmpfile, 0, SEEK_SET)) goto fail;
-        uint64_t num_chunks = data_size / BRA_MAX_CHUNK_SIZE;
-        if (data_size % BRA_MAX_CHUNK_SIZE > 0) ++num_chunks;
+        uint64_t num_chunks = data_size / chunk;
+        if (data_size % chunk > 0) ++num_chunks;
         bra_meta_entry_file_t* mef = (bra_meta_entry_file_t*) me->entry_data;
         mef->data_size             = tmpfile_size;
         me->crc32                  = bra_crc32c(&tmpfile_size, sizeof(tmpfile_size), me->crc32);
@@ -259,7 +309,9 @@ bool bra_io_file_chunks_decompress_file(bra_io_file_t* dst, bra_io_file_t* src, 
     bra_b200_ctx_t* ctx = b200_ctx();
     if (ctx == NULL) return false;
 
-    const uint64_t max_stream = (uint64_t) B200_WINDOW_CHUNKS * (BRA_IO_CHUNK_HEADER_SIZE + BRA_MAX_CHUNK_SIZE);
+    const uint32_t chunk      = b200_chunk_size();
+    const uint32_t wchunks    = b200_window_chunks();
+    const uint64_t max_stream = (uint64_t) wchunks * (BRA_IO_CHUNK_HEADER_SIZE + chunk);
     uint8_t*       stream     = NULL;
     uint8_t*       plain      = NULL;
     uint64_t       file_orig_size = 0;
@@ -267,7 +319,7 @@ bool bra_io_file_chunks_decompress_file(bra_io_file_t* dst, bra_io_file_t* src, 
     if (dst != NULL && (dst->f == NULL || dst->fn == NULL)) goto fail;
     const uint64_t stream_cap = data_size < max_stream ? (data_size ? data_size : 1) : max_stream;
     stream = b200_window(1, stream_cap);
-    if (decode) plain = b200_window(0, _bra_min((uint64_t) B200_WINDOW_CHUNKS, data_size / BRA_IO_CHUNK_HEADER_SIZE + 1) * BRA_MAX_CHUNK_SIZE);
+    if (decode) plain = b200_window(0, _bra_min((uint64_t) wchunks, data_size / BRA_IO_CHUNK_HEADER_SIZE + 1) * chunk);
     if (stream == NULL || (decode && plain == NULL)) goto fail;
 
     for (uint64_t i = 0; i < data_size;)
@@ -275,7 +327,7 @@ bool bra_io_file_chunks_decompress_file(bra_io_file_t* dst, bra_io_file_t* src, 
         /* collect a window of whole chunks: each header names the size of its payload (chunks.c:344-357) */
         uint64_t w = 0;
         uint32_t n = 0;
-        while (n < B200_WINDOW_CHUNKS && i + w < data_size)
+        while (n < wchunks && i + w < data_size)
         {
             uint8_t* h = stream + w;
             if (w + BRA_IO_CHUNK_HEADER_SIZE > stream_cap)
@@ -308,7 +360,7 @@ bool bra_io_file_chunks_decompress_file(bra_io_file_t* dst, bra_io_file_t* src, 
         uint32_t crc        = decode ? me->crc32 : 0;
         /* list mode (chunks.c:369-373): huffman decode + rle size only;
          * otherwise huffman, rle, mtf, bwt decode of every chunk + CRC chain of chunks.c:396-397 */
-        const int rc = decode ? bra_b200_decode_host(ctx, stream, w, plain, (uint64_t) n * BRA_MAX_CHUNK_SIZE, &plain_size, &crc)
+        const int rc = decode ? bra_b200_decode_host(ctx, stream, w, plain, (uint64_t) n * chunk, &plain_size, &crc)
                               : bra_b200_list_host(ctx, stream, w, &plain_size);
         if (rc != 0)
         {

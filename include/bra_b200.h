@@ -85,6 +85,14 @@ int bra_b200_decode_host(bra_b200_ctx_t* ctx, const uint8_t* in, uint64_t in_siz
  * makes its chunk count as 0 bytes. */
 int bra_b200_list_host(bra_b200_ctx_t* ctx, const uint8_t* in, uint64_t in_size, uint64_t* plain_size);
 
+/* Streaming CRC-32C of host memory for the STORED path (reference chunks.c:114-167, which calls bra_crc32c per 256 KiB
+ * piece while copying): _submit enqueues the host-to-device copy and the CRC kernels for `len` bytes (at most 1 GiB) and
+ * returns at once, so the caller can write the piece out and read the next one meanwhile; `data` must stay valid until
+ * _finish, which waits and updates *crc to bra_crc32c(data, len, *crc) (crc may be NULL to just drain). One submission
+ * at a time per context. */
+int bra_b200_crc32c_submit(bra_b200_ctx_t* ctx, const void* data, uint64_t len);
+int bra_b200_crc32c_finish(bra_b200_ctx_t* ctx, uint32_t* crc);
+
 /* Page-locked host memory for the buffers handed to the three calls above: copies to and from it run at the
  * full PCIe rate and overlap the kernels (ordinary memory works too, at a fraction of the rate).
  * bra_b200_host_alloc returns NULL when the memory cannot be locked. */

@@ -31,6 +31,30 @@ def inputs(pkg, golden):
     }
 
 
+def trees(golden):
+    """Multi-entry archives: {archive: (bra arguments, {relative path: bytes})}. `tree` is what the reference's own CLI tests
+    pack (test/test_bra.cpp:310-351: `bra -c -r` over a directory, six empty files): directory entries first, then files in
+    the order of reference src/prog/bra.cpp:337-358; `b.bin` is incompressible, so its entry is first compressed into the
+    temporary file, found not smaller and rewritten STORED (reference chunks.c:268-278, meta_entries.c:194-205)."""
+    vocab = golden["vocab"]
+    tree = {"tree/lorem.txt": bytes.fromhex(golden["blocks"]["lorem_txt"]["in"]),
+            "tree/sub/a.txt": wl.gen_text(300_000, vocab, 31).tobytes(),
+            "tree/sub/b.bin": wl.gen_random(300_000, 32).tobytes(),
+            "tree/sub/deep/c.txt": wl.gen_text(70_000, vocab, 33).tobytes()}
+    for i in range(6):
+        tree[f"tree/e{i}"] = b""
+    return {"tree": (["-c", "-r", "-o", "tree.BRa", "tree"], tree),
+            "stored_only": (["-c", "-o", "stored_only.BRa", "noise.bin"], {"noise.bin": wl.gen_random(600_000, 34).tobytes()})}
+
+
+def write_tree(root, files):
+    for rel, data in files.items():
+        path = os.path.join(root, rel)
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        with open(path, "wb") as f:
+            f.write(data)
+
+
 def main():
     pkg = bra_pkg.load()
     golden = json.load(open(os.path.join(HERE, "reference_vectors.json")))
@@ -48,6 +72,15 @@ def main():
                 e["hex"] = a.hex()
             out["archives"][name] = e
             print(name, len(data), "->", len(a), hex(e["entry_crc32c"]))
+    out["trees"] = {}
+    for name, (argv, files) in trees(golden).items():
+        with tempfile.TemporaryDirectory() as d:
+            write_tree(d, files)
+            subprocess.run([bra] + argv, cwd=d, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            a = open(os.path.join(d, name + ".BRa"), "rb").read()
+            out["trees"][name] = {"size": len(a), "sha256": hashlib.sha256(a).hexdigest(), "entries": int.from_bytes(a[4:8], "little"),
+                                  "input_sha256": hashlib.sha256(b"".join(k.encode() + v for k, v in sorted(files.items()))).hexdigest()}
+            print(name, "->", len(a), "bytes,", out["trees"][name]["entries"], "entries")
     assert out["archives"]["lorem.txt"]["size"] == 1623 and out["archives"]["lorem.txt"]["entry_crc32c"] == 0x74F1DA57
     json.dump(out, open(os.path.join(HERE, "reference_archives.json"), "w"), indent=0, sort_keys=True)
 

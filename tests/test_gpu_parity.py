@@ -294,40 +294,82 @@ def test_batched_native_256k_blocks(pkg, oracle, vocab):
     _check_batch(pkg, oracle, data, block, max_batch=8)
 
 
+def _oracle_blocks(oracle, blocks):
+    """oracle.encode_block over many blocks on all host cores (the C library releases the GIL)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 1) as ex:
+        return list(ex.map(oracle.encode_block, blocks))
+
+
+def _check_device_blocks(pkg, oracle, data: bytes, block: int, max_batch: int, expected=None):
+    """Device path only, EVERY block compared bit for bit (header, payload, CRC) with the oracle's encoder, then decoded
+    back. `expected`: precomputed oracle outputs per block (identical blocks need one oracle call)."""
+    import torch
+    ctx = pkg.Context(0, block, max_batch)
+    try:
+        n = len(data)
+        nblk = (n + block - 1) // block
+        d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
+        hdr, pay, crc = ctx.encode_device(d_in, n)
+        torch.cuda.synchronize()
+        hdr_h = hdr.cpu().numpy().reshape(nblk, 268)
+        crc_h = crc.cpu().numpy().astype(np.uint32)
+        clen = hdr_h[:, 264:268].copy().view(np.uint32).ravel()
+        if expected is None:
+            expected = _oracle_blocks(oracle, [data[b * block:(b + 1) * block] for b in range(nblk)])
+        for b in range(nblk):
+            eh, ep, ec = expected[b]
+            assert int(crc_h[b]) == ec, (b, "crc")
+            assert hdr_h[b].tobytes() == eh, (b, "header", _first_diff(hdr_h[b].tobytes(), eh))
+            got = pay[b * ctx.payload_stride: b * ctx.payload_stride + int(clen[b])].cpu().numpy().tobytes()
+            assert got == ep, (b, _first_diff(got, ep))
+        out, out_len, crc2, status = ctx.decode_device(hdr, pay, nblk)
+        torch.cuda.synchronize()
+        assert int(status.abs().sum()) == 0
+        assert int(out_len.sum()) == n
+        if n == nblk * block:
+            assert torch.equal(out[:n], d_in)
+        else:
+            back = out.cpu().numpy().reshape(nblk, block)
+            lens = out_len.cpu().numpy()
+            for b in range(nblk):
+                assert back[b, :lens[b]].tobytes() == data[b * block:(b + 1) * block], b
+        assert (crc2.cpu().numpy().astype(np.uint32) == crc_h).all()
+        return ctx.stats(), hdr_h
+    finally:
+        ctx.close()
+
+
 def test_batched_1mib_text_and_random(pkg, oracle, vocab):
-    """BASELINE configs 2 and 3 at full block size: a few blocks compared bit for bit with the oracle,
-    all blocks round-tripped."""
+    """BASELINE configs 2 and 3 at full block size: 64 blocks of each shape, EVERY block compared bit for bit with
+    the oracle's encoder (header, code lengths, payload, CRC) and decoded back; a mixed batch also goes through the host path."""
     block = 1 << 20
-    data = _text(pkg, vocab, 6 * block) + wl.gen_random(2 * block, 2).tobytes()
-    st = _check_batch(pkg, oracle, data, block, max_batch=8, full_compare_blocks=[0, 5, 6])
+    text = _text(pkg, vocab, 64 * block, seed=1)
+    st, _ = _check_device_blocks(pkg, oracle, text, block, max_batch=64)
     assert st["bwt_rounds"] >= 1
+    rnd = wl.gen_random(64 * block, 3).tobytes()
+    _check_device_blocks(pkg, oracle, rnd, block, max_batch=48)  # two internal batches
+    mixed = text[:3 * block] + rnd[:2 * block] + text[5 * block:5 * block + 12345]
+    _check_batch(pkg, oracle, mixed, block, max_batch=8)
 
 
 def test_batched_8mib_periodic(pkg, oracle):
-    """BASELINE config 4: exactly periodic (n/16-way rotation ties -> primary 0) and long-repeat blocks."""
-    import torch
+    """BASELINE config 4 at the full 8 MiB block size, compared with the oracle's ENCODER (fast BWT + the linear stages),
+    not just decoded by it: C4a exactly periodic (n/16-way rotation ties -> primary 0; every block of the workload is this
+    block), C4b a 251-byte pattern repeated (all rotations distinct, LCP ~ n, deepest Huffman tables of the BASELINE
+    shapes): the first blocks of the 1 GiB workload, whose phases differ because 251 does not divide the block."""
     block = 8 << 20
-    nrng = np.random.default_rng(4)
-    a = b"0123456789abcdef" * (block // 16)
-    pat = bytes(nrng.integers(0, 256, 251, dtype=np.uint8))
-    ctx = pkg.Context(0, block, 2)
-    try:
-        for data, primary in ((a, 0), ((pat * (block // 251 + 1))[:block], None)):
-            d_in = torch.frombuffer(bytearray(data), dtype=torch.uint8).cuda()
-            hdr, pay, crc = ctx.encode_device(d_in, block)
-            h = hdr.cpu().numpy()
-            if primary is not None:
-                assert int.from_bytes(h[:4].tobytes(), "little") == primary
-            # the oracle's linear-time decode chain must reproduce the input from the GPU-encoded block
-            c = int.from_bytes(h[264:268].tobytes(), "little")
-            plain = oracle.decode_block(h.tobytes(), pay[:c].cpu().numpy().tobytes(), block)
-            assert plain == data, _first_diff(plain, data)
-            assert int(crc.cpu().numpy().astype(np.uint32)[0]) == oracle.crc32c(data)
-            out, out_len, crc2, status = ctx.decode_device(hdr, pay, 1)
-            assert int(status[0]) == 0 and int(out_len[0]) == block
-            assert out.cpu().numpy().tobytes() == data
-    finally:
-        ctx.close()
+    a = wl.gen_periodic(block, wl.HEX16).tobytes()
+    exp_a = oracle.encode_block(a)
+    assert int.from_bytes(exp_a[0][:4], "little") == 0
+    _, hdr_h = _check_device_blocks(pkg, oracle, a * 3, block, max_batch=2, expected=[exp_a] * 3)
+    assert all(int.from_bytes(hdr_h[b, :4].tobytes(), "little") == 0 for b in range(3))
+    nb = 4
+    c4b = wl.gen_periodic(nb * block, wl.repeat251_pattern()).tobytes()
+    _check_device_blocks(pkg, oracle, c4b, block, max_batch=nb)
+    # host path + CRC chain + list mode on one block of each
+    _check_batch(pkg, oracle, a + c4b[block:2 * block], block, max_batch=2, full_compare_blocks=[])
 
 
 def test_decode_rejects_corrupt_blocks(pkg, oracle, vocab):
@@ -395,8 +437,8 @@ def test_reference_unit_test_programs_pass_against_the_dropin(golden, tmp_path):
         r = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=300)
         assert r.returncode == 0, (name, r.stdout[-2000:], r.stderr[-2000:])
         ran += 1
-    if ran == 0:
-        pytest.skip("oracle/_ref test programs not built (needs /root/reference at build time)")
+    # under -m gpu a missing prebuilt program is a failure, never a skip: the binaries travel with the snapshot
+    assert ran == 2, "oracle/_ref/test_bra_encoders / test_bra_crc32c missing: run __graft_entry__.build() where /root/reference exists"
 
 
 def test_batched_fuzz_shapes(pkg, oracle, vocab):
@@ -470,8 +512,7 @@ def test_reference_cli_packs_identical_archives_with_the_dropin(pkg, golden, tmp
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     bra, unbra = os.path.join(root, "oracle", "_ref", "bra_" + suffix), os.path.join(root, "oracle", "_ref", "unbra_" + suffix)
-    if not (os.path.exists(bra) and os.path.exists(unbra)):
-        pytest.skip("oracle/_ref CLI binaries not built (needs /root/reference at build time)")
+    assert os.path.exists(bra) and os.path.exists(unbra), "oracle/_ref CLI binaries missing: run __graft_entry__.build() where /root/reference exists"
     sys.path.insert(0, os.path.join(root, "tests", "golden"))
     from make_golden_archives import inputs
     arcs = json.load(open(os.path.join(root, "tests", "golden", "reference_archives.json")))["archives"]
@@ -493,3 +534,41 @@ def test_reference_cli_packs_identical_archives_with_the_dropin(pkg, golden, tmp
         r = subprocess.run([unbra, "-y", "-o", "out", name + ".BRa"], cwd=tmp_path, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, (name, r.stdout[-1500:], r.stderr[-1500:])
         assert (tmp_path / "out" / name).read_bytes() == data, name
+
+
+@pytest.mark.parametrize("suffix", ["gpu", "gpu2"])
+def test_reference_cli_directory_tree_stored_fallback_and_empty_files(golden, tmp_path, suffix):
+    """The reference's own `bra -c -r` over a directory tree (reference test/test_bra.cpp:310-351; entry order of
+    src/prog/bra.cpp:337-358): directory entries, six empty files, three compressible files and one incompressible file whose
+    entry is compressed first, found not smaller and rewritten STORED (chunks.c:268-278, meta_entries.c:194-205) -- the seam's
+    copy_file with the CRC on the GPU. The archive must be byte-identical to the unmodified reference's; `unbra` must list,
+    test and extract every entry. `stored_only` is a single incompressible file (the whole archive takes the STORED path)."""
+    import hashlib
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    bra, unbra = os.path.join(root, "oracle", "_ref", "bra_" + suffix), os.path.join(root, "oracle", "_ref", "unbra_" + suffix)
+    assert os.path.exists(bra) and os.path.exists(unbra), "oracle/_ref CLI binaries missing: run __graft_entry__.build() where /root/reference exists"
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from make_golden_archives import trees, write_tree
+    exp_all = json.load(open(os.path.join(root, "tests", "golden", "reference_archives.json")))["trees"]
+    for name, (argv, files) in trees(golden).items():
+        exp = exp_all[name]
+        work = tmp_path / (name + "_" + suffix)
+        work.mkdir()
+        write_tree(str(work), files)
+        r = subprocess.run([bra] + argv, cwd=work, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (name, r.stdout[-1500:], r.stderr[-1500:])
+        got = (work / (name + ".BRa")).read_bytes()
+        assert len(got) == exp["size"], (name, len(got), exp["size"])
+        assert int.from_bytes(got[4:8], "little") == exp["entries"], name
+        assert hashlib.sha256(got).hexdigest() == exp["sha256"], name
+        for flag in ("-l", "-t"):
+            r = subprocess.run([unbra, flag, name + ".BRa"], cwd=work, capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, (name, flag, r.stdout[-1500:], r.stderr[-1500:])
+        r = subprocess.run([unbra, "-y", "-o", "out", name + ".BRa"], cwd=work, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, (name, r.stdout[-1500:], r.stderr[-1500:])
+        for rel, data in files.items():
+            assert (work / "out" / rel).read_bytes() == data, (name, rel)
