@@ -211,10 +211,14 @@ inline std::vector<uint32_t> stage_plan(uint64_t nblk, uint32_t hb)
 // Three streams: input copies run one stage ahead of the kernels, output copies one stage behind
 // (double-buffered device staging). The kernels' own host syncs (BWT round control) only block the
 // host thread; the copy streams keep moving underneath.
-extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64_t total, uint8_t* out, uint64_t out_cap, uint64_t* out_size,
-                                    uint32_t* crc_chain)
+namespace bra {
+// `place(user, bytes)` names the host destination of the next `bytes` stream bytes (nullptr: no room). The plain entry
+// point hands out consecutive pieces of the caller's buffer; the multi-GPU pool (pool.cu) first waits until the sizes of
+// all earlier block ranges are known, so that every range lands at its final offset of the ordered stream.
+int encode_host_impl(bra_b200_ctx_t* c, const uint8_t* in, uint64_t total, uint8_t* (*place)(void*, uint64_t), void* user, uint64_t* out_size,
+                     uint32_t* crc_chain)
 {
-    if (!c || !in || !out || !out_size || total == 0)
+    if (!c || !in || !place || !out_size || total == 0)
     {
         bra_b200_log_error("bra_b200_encode_host: invalid arguments");
         return 1;
@@ -287,13 +291,14 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
         memcpy(&str_size, mail, 8);
         BRA_TRACE("encode stage %llu: kernels done, %llu stream bytes", (unsigned long long) i, (unsigned long long) str_size);
         memcpy(h_crc.data(), mail + 16, (size_t) 2 * HB * 4);
-        if (produced + str_size > out_cap)
+        uint8_t* dst = place(user, str_size);
+        if (!dst)
         {
             bra_b200_log_error("bra_b200_encode_host: output buffer too small");
             return 6;
         }
         cudaStreamWaitEvent(P.s_out, P.ev_comp[slot], 0);
-        if (cudaMemcpyAsync(out + produced, d_str[slot], str_size, cudaMemcpyDeviceToHost, P.s_out) != cudaSuccess) return 4;
+        if (cudaMemcpyAsync(dst, d_str[slot], str_size, cudaMemcpyDeviceToHost, P.s_out) != cudaSuccess) return 4;
         cudaEventRecord(P.ev_out[slot], P.s_out);
         // CRC chain of reference chunks.c:248-249 while the copy runs
         for (uint32_t b = 0; b < nb; ++b)
@@ -309,6 +314,35 @@ extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64
     *out_size = produced;
     if (crc_chain) *crc_chain = crc;
     return 0;
+}
+}  // namespace bra
+
+namespace {
+struct LinearSink
+{
+    uint8_t* out;
+    uint64_t cap, used;
+};
+uint8_t* linear_place(void* user, uint64_t bytes)
+{
+    LinearSink* s = static_cast<LinearSink*>(user);
+    if (s->used + bytes > s->cap) return nullptr;
+    uint8_t* p = s->out + s->used;
+    s->used += bytes;
+    return p;
+}
+}  // namespace
+
+extern "C" int bra_b200_encode_host(bra_b200_ctx_t* c, const uint8_t* in, uint64_t total, uint8_t* out, uint64_t out_cap, uint64_t* out_size,
+                                    uint32_t* crc_chain)
+{
+    if (!out)
+    {
+        bra_b200_log_error("bra_b200_encode_host: invalid arguments");
+        return 1;
+    }
+    LinearSink s{out, out_cap, 0};
+    return encode_host_impl(c, in, total, linear_place, &s, out_size, crc_chain);
 }
 
 // sizes_only: list mode of the reference (chunks.c:369-373) -- Huffman decode + RLE size pass, nothing is copied back

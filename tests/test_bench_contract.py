@@ -20,6 +20,9 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["unit"].startswith("GB/s") and d["data"] == "synthetic" and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["product_library_mapped"] is False  # workload generators live outside libbra_b200.so
+    assert set(d["per_workload"]) == {"text", "random", "periodic16_8mib", "repeat251_8mib"}
+    assert all(v["value"] > 0 for v in d["per_workload"].values())
 
 
 def test_reference_arm_other_ranks_exit_quietly():
