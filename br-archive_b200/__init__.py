@@ -42,6 +42,8 @@ BATCH_API = [
     "bra_b200_payload_stride", "bra_b200_workspace_bytes", "bra_b200_last_stats", "bra_b200_encode_device", "bra_b200_decode_device",
     "bra_b200_encode_bound", "bra_b200_encode_host", "bra_b200_decode_host", "bra_b200_list_host", "bra_b200_host_alloc", "bra_b200_host_free", "bra_b200_crc32c_submit", "bra_b200_crc32c_finish",
     "bra_b200_prof_enable", "bra_b200_prof_reset", "bra_b200_prof_count", "bra_b200_prof_read",
+    "bra_b200_pool_create", "bra_b200_pool_destroy", "bra_b200_pool_workers", "bra_b200_pool_worker_ranges", "bra_b200_pool_encode_bound",
+    "bra_b200_pool_encode_host", "bra_b200_pool_decode_host",
 ]
 
 
@@ -90,6 +92,23 @@ def lib() -> C.CDLL:
     L.bra_b200_decode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), u32p]
     L.bra_b200_list_host.restype = C.c_int
     L.bra_b200_list_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.bra_b200_crc32c_submit.restype = C.c_int
+    L.bra_b200_crc32c_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    L.bra_b200_crc32c_finish.restype = C.c_int
+    L.bra_b200_crc32c_finish.argtypes = [C.c_void_p, u32p]
+    L.bra_b200_pool_create.restype = C.c_void_p
+    L.bra_b200_pool_create.argtypes = [C.POINTER(C.c_int), C.c_int, C.c_uint32, C.c_uint32, C.c_int]
+    L.bra_b200_pool_destroy.argtypes = [C.c_void_p]
+    L.bra_b200_pool_workers.restype = C.c_int
+    L.bra_b200_pool_workers.argtypes = [C.c_void_p]
+    L.bra_b200_pool_worker_ranges.restype = C.c_int
+    L.bra_b200_pool_worker_ranges.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), u32p]
+    L.bra_b200_pool_encode_bound.restype = C.c_uint64
+    L.bra_b200_pool_encode_bound.argtypes = [C.c_void_p, C.c_uint64]
+    L.bra_b200_pool_encode_host.restype = C.c_int
+    L.bra_b200_pool_encode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), u32p]
+    L.bra_b200_pool_decode_host.restype = C.c_int
+    L.bra_b200_pool_decode_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64), u32p]
     L.bra_b200_prof_enable.argtypes = [C.c_int]
     L.bra_b200_prof_count.restype = C.c_int
     L.bra_b200_prof_read.restype = C.c_int
@@ -265,3 +284,67 @@ class Context:
         if rc != 0:
             raise RuntimeError(f"bra_b200_list_host failed with code {rc}")
         return int(osz.value)
+
+
+def _ptr_len(a):
+    return (a.ctypes.data if hasattr(a, "ctypes") else a.data_ptr()), (int(a.nbytes) if hasattr(a, "nbytes") else int(a.numel()))
+
+
+class Pool:
+    """One job over several GPUs of this process (include/bra_b200.h, bra_b200_pool_*): the block list of one input is cut
+    into ranges that per-GPU workers take from a shared queue; output is the ordered chunk stream and the folded CRC chain,
+    byte-identical to a single context's."""
+
+    def __init__(self, devices, block_size: int = 1 << 20, range_blocks: int = 64, workers_per_device: int = 2):
+        self.L = lib()
+        arr = (C.c_int * len(devices))(*devices)
+        self.handle = self.L.bra_b200_pool_create(arr, len(devices), block_size, range_blocks, workers_per_device)
+        if not self.handle:
+            raise RuntimeError("bra_b200_pool_create failed (no CUDA device, or out of device memory); there is no CPU fallback")
+        self.block_size = block_size
+
+    def close(self):
+        if self.handle:
+            self.L.bra_b200_pool_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def encode_bound(self, total: int) -> int:
+        return int(self.L.bra_b200_pool_encode_bound(self.handle, total))
+
+    def stats(self):
+        out = []
+        for w in range(self.L.bra_b200_pool_workers(self.handle)):
+            d, r = C.c_int(0), C.c_uint32(0)
+            self.L.bra_b200_pool_worker_ranges(self.handle, w, C.byref(d), C.byref(r))
+            out.append({"worker": w, "device": d.value, "ranges": r.value})
+        return out
+
+    def encode_host(self, data, out=None, crc_chain: int = 0):
+        import numpy as np
+        ptr, n = _ptr_len(data)
+        if out is None:
+            out = np.empty(self.encode_bound(n), dtype=np.uint8)
+        optr, ocap = _ptr_len(out)
+        osz, crc = C.c_uint64(0), C.c_uint32(crc_chain)
+        rc = self.L.bra_b200_pool_encode_host(self.handle, ptr, n, optr, ocap, C.byref(osz), C.byref(crc))
+        if rc != 0:
+            raise RuntimeError(f"bra_b200_pool_encode_host failed with code {rc}")
+        return out[: osz.value], int(crc.value)
+
+    def decode_host(self, stream_bytes, out_cap: int, out=None, crc_chain: int = 0):
+        import numpy as np
+        ptr, n = _ptr_len(stream_bytes)
+        if out is None:
+            out = np.empty(max(out_cap, 1), dtype=np.uint8)
+        optr, _ = _ptr_len(out)
+        osz, crc = C.c_uint64(0), C.c_uint32(crc_chain)
+        rc = self.L.bra_b200_pool_decode_host(self.handle, ptr, n, optr, out_cap, C.byref(osz), C.byref(crc))
+        if rc != 0:
+            raise RuntimeError(f"bra_b200_pool_decode_host failed with code {rc}")
+        return out[: osz.value], int(crc.value)

@@ -17,4 +17,7 @@ uint8_t* ctx_io_buffer(bra_b200_ctx* c, uint64_t bytes);
 cudaStream_t ctx_stream(bra_b200_ctx* c);
 uint32_t* ctx_mail_host(bra_b200_ctx* c);  // pinned, device-visible words for the host path (8*max_batch + 16)
 int ctx_device(const bra_b200_ctx* c);
+// bra_b200_encode_host with the destination of every stage's stream bytes named by `place` (hostpath.cu; used by pool.cu)
+int encode_host_impl(bra_b200_ctx_t* c, const uint8_t* in, uint64_t total, uint8_t* (*place)(void*, uint64_t), void* user, uint64_t* out_size,
+                     uint32_t* crc_chain);
 }  // namespace bra

@@ -85,6 +85,24 @@ int bra_b200_decode_host(bra_b200_ctx_t* ctx, const uint8_t* in, uint64_t in_siz
  * makes its chunk count as 0 bytes. */
 int bra_b200_list_host(bra_b200_ctx_t* ctx, const uint8_t* in, uint64_t in_size, uint64_t* plain_size);
 
+/* ---- one job over several GPUs of ONE process (BASELINE config 5) ------------------------------------
+ * A pool owns `workers_per_device` contexts on each of the listed devices (the same device may be listed more
+ * than once). bra_b200_pool_encode_host / _decode_host behave exactly like the single-context calls above --
+ * same chunk stream, same CRC chain -- but the block list of the input is cut into ranges of `range_blocks`
+ * blocks that the workers take from a shared queue; every range lands at its final offset of the ordered
+ * stream and the per-range CRC chains are folded with bra_crc32c_combine. There is no inter-GPU collective. */
+typedef struct bra_b200_pool bra_b200_pool_t;
+bra_b200_pool_t* bra_b200_pool_create(const int* devices, int ndev, uint32_t block_size, uint32_t range_blocks, int workers_per_device);
+void             bra_b200_pool_destroy(bra_b200_pool_t* pool);
+int              bra_b200_pool_workers(const bra_b200_pool_t* pool);
+/* device and number of ranges worker `worker` processed in the last call */
+int      bra_b200_pool_worker_ranges(const bra_b200_pool_t* pool, int worker, int* device, uint32_t* ranges);
+uint64_t bra_b200_pool_encode_bound(const bra_b200_pool_t* pool, uint64_t total);
+int bra_b200_pool_encode_host(bra_b200_pool_t* pool, const uint8_t* in, uint64_t total, uint8_t* out, uint64_t out_cap, uint64_t* out_size,
+                              uint32_t* crc_chain);
+int bra_b200_pool_decode_host(bra_b200_pool_t* pool, const uint8_t* in, uint64_t in_size, uint8_t* out, uint64_t out_cap, uint64_t* out_size,
+                              uint32_t* crc_chain);
+
 /* Streaming CRC-32C of host memory for the STORED path (reference chunks.c:114-167, which calls bra_crc32c per 256 KiB
  * piece while copying): _submit enqueues the host-to-device copy and the CRC kernels for `len` bytes (at most 1 GiB) and
  * returns at once, so the caller can write the piece out and read the next one meanwhile; `data` must stay valid until

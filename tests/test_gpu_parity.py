@@ -572,3 +572,55 @@ def test_reference_cli_directory_tree_stored_fallback_and_empty_files(golden, tm
         assert r.returncode == 0, (name, r.stdout[-1500:], r.stderr[-1500:])
         for rel, data in files.items():
             assert (work / "out" / rel).read_bytes() == data, (name, rel)
+
+
+# ------------------------------------------------------------------------------------------ one job over several GPUs
+def test_pool_shards_one_input_and_matches_the_single_gpu_stream(pkg, oracle, vocab):
+    """BASELINE config 5 / SURVEY 8(e): ONE input whose block list is sharded over the GPUs of this process by bra_b200_pool
+    (two workers per device, dynamic block-range queue). The ordered chunk stream and the folded CRC chain must be
+    byte-identical to a single context's, which _check_batch elsewhere ties to the oracle; the CRC chain is also recomputed
+    here with the oracle exactly as reference chunks.c:248-249 composes it. Uses GPUs 0 and 1 when the box has two (on a
+    one-GPU box both shards run on GPU 0: same code path, same ordering logic)."""
+    import torch
+    rng = random.Random(5)
+    block = 65536
+    ndev = torch.cuda.device_count()
+    devices = [0, 1] if ndev >= 2 else [0, 0]
+    pat = wl.repeat251_pattern()
+    data = (_text(pkg, vocab, 9 * block, seed=3) + wl.gen_random(5 * block, 7).tobytes() + (pat * (3 * block // 251 + 1))[:3 * block]  # slow ranges in the middle
+            + wl.HEX16 * (2 * block // 16) + _runs(rng, 4 * block) + _text(pkg, vocab, 6 * block + 4321, seed=4))
+    single = pkg.Context(0, block, 16)
+    pool = pkg.Pool(devices, block, range_blocks=4, workers_per_device=2)
+    try:
+        arr = np.frombuffer(data, dtype=np.uint8)
+        s1, c1 = single.encode_host(arr, crc_chain=0x1234ABCD)
+        for _ in range(2):  # twice: the contexts are reused
+            s2, c2 = pool.encode_host(arr, crc_chain=0x1234ABCD)
+            assert s2.tobytes() == s1.tobytes(), _first_diff(s2.tobytes(), s1.tobytes())
+            assert c2 == c1
+        nblk = (len(data) + block - 1) // block
+        st = pool.stats()
+        assert sum(w["ranges"] for w in st) == (nblk + 3) // 4 and {w["device"] for w in st} == set(devices)
+        # the chain against the oracle (header CRC then block CRC per chunk, reference chunks.c:248-249)
+        chain, pos, starts = 0x1234ABCD, 0, []
+        sb = s1.tobytes()
+        for b in range(nblk):
+            starts.append(pos)
+            c = int.from_bytes(sb[pos + 263:pos + 267], "little")
+            hdr268 = sb[pos:pos + 3] + b"\x00" + sb[pos + 3:pos + 267]
+            chain = oracle.crc32c(hdr268, chain)
+            chain = oracle.crc32c(data[b * block:(b + 1) * block], chain)
+            pos += 267 + c
+        assert pos == len(sb) and chain == c1
+        p2, d2 = pool.decode_host(s2, len(data), crc_chain=0x1234ABCD)
+        assert p2.tobytes() == data and d2 == c1
+        p1, d1 = single.decode_host(s1, len(data), crc_chain=0x1234ABCD)
+        assert p1.tobytes() == data and d1 == c1
+        # a corrupt chunk in the middle of the stream fails the pooled call like the single one
+        bad = bytearray(sb)
+        bad[starts[nblk // 2]:starts[nblk // 2] + 3] = b"\xff\xff\xff"  # primary index beyond the block (reference chunks.c:385-389)
+        with pytest.raises(RuntimeError):
+            pool.decode_host(np.frombuffer(bytes(bad), dtype=np.uint8), len(data))
+    finally:
+        pool.close()
+        single.close()
