@@ -174,7 +174,7 @@ def parity_sample(kind, block, host, nblk, hdr, pay, crc, payload_stride, want):
 
 
 # algorithmic bytes one launch of each batch-wide kernel family moves, per element of the batch
-ALG_PER_ELEM = {"radix_scatter": 16, "radix_hist": 4, "radix_scatter_u8": 5, "mtf_apply": 2, "mtf_summary": 1, "bwt_ranks": 9, "bwt_heads": 9,
+ALG_PER_ELEM = {"radix_scatter": 16, "radix_scatter_implicit": 12, "radix_hist": 1, "radix_scatter_u8": 5, "mtf_apply": 2, "mtf_summary": 1, "bwt_ranks": 9, "bwt_heads": 9,
                 "bwt_prepare": 16, "bwt_finish": 10, "bwt_gather": 6, "crc32c": 1, "ibwt_walk_len": 4, "ibwt_walk_emit": 5}
 
 

@@ -12,7 +12,7 @@ namespace bra {
 // ---- prof.cu: launch accounting (see include/bra_b200.h, bra_b200_prof_*) ------------------------
 enum ProfId
 {
-    P_CRC, P_RS_HIST, P_RS_SCAN, P_RS_SCATTER, P_RS_SCATTER_U8, P_BWT_PERIOD, P_BWT_KEYS, P_BWT_HEADS, P_BWT_RANKS, P_BWT_PREPARE, P_BWT_GATHER, P_BWT_FINISH, P_BWT_MISC,
+    P_CRC, P_RS_HIST, P_RS_SCATTER_IMPL, P_RS_SCATTER, P_RS_SCATTER_U8, P_BWT_PERIOD, P_BWT_KEYS, P_BWT_HEADS, P_BWT_RANKS, P_BWT_PREPARE, P_BWT_GATHER, P_BWT_FINISH, P_BWT_MISC,
     P_MTF_SUMMARY, P_MTF_SCAN, P_MTF_APPLY, P_RLE_ENC_HEADS, P_RLE_ENC_LIT, P_RLE_ENC_SIZE, P_RLE_ENC_EMIT, P_RLE_DEC_EXIT, P_RLE_DEC_CHAIN,
     P_RLE_DEC_MARK, P_RLE_DEC_EXPAND, P_HUF_HIST, P_HUF_BUILD, P_HUF_BITS, P_HUF_PACK, P_HUF_DEC_TABLES, P_HUF_DEC_SYNC, P_HUF_DEC_SCAN,
     P_HUF_DEC_WRITE, P_HUF_DEC_TRAILING, P_IBWT_WALK_LEN, P_IBWT_STITCH, P_IBWT_WALK_EMIT, P_GLUE, P_COUNT
@@ -38,16 +38,23 @@ bool crc_blocks(const uint8_t* d_in, uint64_t stride, const uint32_t* d_len, uin
 bool crc_headers(const uint8_t* d_hdr, uint32_t item_bytes, uint32_t nitems, uint32_t* d_out, cudaStream_t st);
 
 // ---- sort.cu ------------------------------------------------------------------------------
+// One stable 8-bit LSD pass = one kernel (decoupled look-back over tiles, values staged by bulk-asynchronous copies).
+// `d_hist` is the sort workspace of radix_hist_bytes() bytes. Its first nblk * RS_GHIST_STRIDE words are the digit
+// histograms of every block, [b][pass][256], which the producer of the keys must have filled for all passes of the
+// sort before the first pass is launched (zeroed by the producer; pass p looks at bits [8p, 8p+8) of the key).
+#define RS_GHIST_PASSES 4
+#define RS_GHIST_STRIDE (RS_GHIST_PASSES * 256)
 size_t radix_hist_bytes(uint32_t max_len, uint32_t nblk);
 // small host <-> device transfers done by a copy kernel through pinned, device-visible host memory: a cudaMemcpyAsync of
 // a few bytes would wait on its copy engine behind the bulk copies of the neighbouring pipeline stages
 bool mail_fetch(uint32_t* d_dst, const uint32_t* h_src, uint32_t words, cudaStream_t st);
 bool mail_publish(uint32_t* h_dst, const uint32_t* d_src, uint32_t words, cudaStream_t st);
-bool   radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t stride,
-                      const uint32_t* d_len, const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t shift, uint32_t bits, bool hist_ready,
-                      uint32_t* d_hist, cudaStream_t st);
-bool   radix_pass_u8_index_packed(const uint8_t* keys, uint32_t* packed_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len,
-                                  uint32_t nblk, uint32_t* d_hist, cudaStream_t st);
+// vals == nullptr: the values are the element indices (first pass of a sort)
+bool radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t stride, const uint32_t* d_len,
+                    const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t pass, uint32_t* d_hist, cudaStream_t st);
+// u8 keys, implicit index values, output word (index << 8) | key; computes its own histogram
+bool radix_pass_u8_index_packed(const uint8_t* keys, uint32_t* packed_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len,
+                                uint32_t nblk, uint32_t* d_hist, cudaStream_t st);
 
 // ---- bwt.cu -------------------------------------------------------------------------------
 struct BwtFwdArgs

@@ -148,21 +148,16 @@ __global__ void __launch_bounds__(256) bwt_alpha_codes_kernel(uint8_t* __restric
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t* __restrict__ in, uint64_t stride,
                                                                    const uint32_t* __restrict__ period, const uint8_t* __restrict__ alpha,
-                                                                   uint32_t cbits, uint32_t* __restrict__ keys, uint32_t tiles,
-                                                                   uint32_t* __restrict__ hist)
+                                                                   uint32_t cbits, uint32_t* __restrict__ keys, uint32_t npass,
+                                                                   uint32_t* __restrict__ ghist)
 {
-    __shared__ uint32_t sh[256];
+    __shared__ uint32_t sh[RS_GHIST_STRIDE];  // digit histograms of every radix pass of the sort that follows
     __shared__ uint8_t  code[256];
     const uint32_t b = blockIdx.y;
     const uint32_t p = period[b];
     const uint32_t tile0 = blockIdx.x * EW_TILE;
-    uint32_t*      hout  = hist + ((uint64_t) b * 256) * tiles + blockIdx.x;  // histogram of the first radix pass (shift 0)
-    if (tile0 >= p)
-    {
-        hout[(uint64_t) threadIdx.x * tiles] = 0;
-        return;
-    }
-    sh[threadIdx.x]   = 0;
+    if (tile0 >= p) return;
+    for (uint32_t i = threadIdx.x; i < npass * 256; i += EW_THREADS) sh[i] = 0;
     code[threadIdx.x] = alpha ? alpha[(uint64_t) b * 256 + threadIdx.x] : (uint8_t) threadIdx.x;
     __syncthreads();
     const uint8_t* T    = in + (uint64_t) b * stride;
@@ -179,11 +174,34 @@ __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t
             for (int d = 0; d < 4; ++d) key = (key << cbits) | code[T[(j + d) % p]];
         }
         keys[base + j] = key;
-        atomicAdd(&sh[key & 0xFFu], 1u);
+        for (uint32_t ps = 0; ps < npass; ++ps) atomicAdd(&sh[ps * 256 + ((key >> (8 * ps)) & 0xFFu)], 1u);
     }
     __syncthreads();
-    hout[(uint64_t) threadIdx.x * tiles] = sh[threadIdx.x];
+    for (uint32_t i = threadIdx.x; i < npass * 256; i += EW_THREADS)
+        if (sh[i]) atomicAdd(&ghist[(uint64_t) b * RS_GHIST_STRIDE + i], sh[i]);
 }
+
+// Digit histograms of the ranks a doubling round sorts on. The keys of the round are rank[SA[j] - h] over all j, i.e.
+// every rank exactly once, so the kernel that assigns the ranks counts their digits: runs of equal ranks (the members of
+// one group are neighbours) are counted with one shared-memory atomic per pass.
+struct RankHist
+{
+    uint32_t* sh;
+    uint32_t  npass, val, cnt;
+    __device__ __forceinline__ RankHist(uint32_t* s, uint32_t np) : sh(s), npass(np), val(0), cnt(0) {}
+    __device__ __forceinline__ void flush()
+    {
+        if (cnt)
+            for (uint32_t ps = 0; ps < npass; ++ps) atomicAdd(&sh[ps * 256 + ((val >> (8 * ps)) & 0xFFu)], cnt);
+        cnt = 0;
+    }
+    __device__ __forceinline__ void add(uint32_t v)
+    {
+        if (v != val) flush();
+        val = v;
+        ++cnt;
+    }
+};
 
 // ------------------------------------------------------------------------------------------------
 // 3. group heads and ranks
@@ -316,15 +334,17 @@ __global__ void __launch_bounds__(EW_THREADS)
 __global__ void __launch_bounds__(EW_THREADS)
     bwt_dense_ranks_kernel(const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags, uint64_t stride, const uint32_t* __restrict__ period,
                            const uint8_t* __restrict__ skip, const uint32_t* __restrict__ tile_heads, uint32_t tiles, uint32_t* __restrict__ rank_out,
-                           const uint32_t* __restrict__ ngroups)
+                           const uint32_t* __restrict__ ngroups, uint32_t npass, uint32_t* __restrict__ ghist)
 {
     __shared__ uint32_t red[34];
+    __shared__ uint32_t sh[RS_GHIST_STRIDE];
     const uint32_t b = blockIdx.y;
     if (skip[b]) return;
     const uint32_t p = period[b];
     if (ngroups[b] >= p) return;  // finished: nobody will read its ranks
     const uint32_t tile0 = blockIdx.x * EW_TILE;
     if (tile0 >= p) return;
+    for (uint32_t i = threadIdx.x; i < npass * 256; i += EW_THREADS) sh[i] = 0;
     const uint64_t base = (uint64_t) b * stride;
     uint32_t       before = 0;
     for (uint32_t t = threadIdx.x; t < blockIdx.x; t += EW_THREADS) before += tile_heads[(uint64_t) b * tiles + t];
@@ -336,11 +356,17 @@ __global__ void __launch_bounds__(EW_THREADS)
     for (uint32_t i = 0; i < m; ++i)
         if (flags[base + j0 + i]) mask |= 1u << i;
     uint32_t run = carry + block_excl_add((uint32_t) __popc(mask), red, nullptr);  // heads before my first slot
+    RankHist rh(sh, npass);
     for (uint32_t i = 0; i < m; ++i)
     {
         run += (mask >> i) & 1u;
         rank_out[base + sa[base + j0 + i]] = run - 1u;  // slot 0 is a head, so run >= 1 here
+        rh.add(run - 1u);
     }
+    rh.flush();
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < npass * 256; i += EW_THREADS)
+        if (sh[i]) atomicAdd(&ghist[(uint64_t) b * RS_GHIST_STRIDE + i], sh[i]);
 }
 
 // Pass B: rank[SA[j]] = index of the head of j's group, in place. Slots that were singleton groups
@@ -352,9 +378,10 @@ __global__ void __launch_bounds__(EW_THREADS)
     bwt_ranks_kernel(const uint32_t* __restrict__ sa, const uint8_t* __restrict__ flags, const uint8_t* __restrict__ flags_old, uint64_t stride,
                      const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, const int* __restrict__ tile_last, uint32_t tiles,
                      uint32_t* __restrict__ rank_out, uint32_t* __restrict__ maxgroup, unsigned long long* __restrict__ sumsq,
-                     const uint32_t* __restrict__ ngroups)
+                     const uint32_t* __restrict__ ngroups, uint32_t npass, uint32_t* __restrict__ ghist /* WHAT 2: digit histograms of the ranks */)
 {
-    __shared__ int red[33];
+    __shared__ int      red[33];
+    __shared__ uint32_t sh[WHAT == 2 ? RS_GHIST_STRIDE : 1];
     const uint32_t b = blockIdx.y;
     if (skip[b]) return;
     const uint32_t p     = period[b];
@@ -362,6 +389,8 @@ __global__ void __launch_bounds__(EW_THREADS)
     const uint32_t tile0 = blockIdx.x * EW_TILE;
     if (tile0 >= p) return;
     const uint64_t base = (uint64_t) b * stride;
+    if (WHAT == 2)
+        for (uint32_t i = threadIdx.x; i < npass * 256; i += EW_THREADS) sh[i] = 0;
 
     // carry-in: last head before this tile
     int carry = 0;
@@ -392,6 +421,7 @@ __global__ void __launch_bounds__(EW_THREADS)
     // group statistics for the finisher decision: every head closes the group before it
     uint32_t           mg = 0;
     unsigned long long sq = 0;
+    RankHist           rh(sh, WHAT == 2 ? npass : 0u);
     for (uint32_t i = 0; i < m; ++i)
     {
         if (newmask & (1u << i))
@@ -407,8 +437,16 @@ __global__ void __launch_bounds__(EW_THREADS)
         }
         const bool settled = ((oldmask >> i) & 3u) == 3u;  // was a singleton group already: rank unchanged
         if (WHAT != 1 && !settled) rank_out[base + sa[base + j0 + i]] = (uint32_t) run;
+        if (WHAT == 2) rh.add((uint32_t) run);
     }
-    if (WHAT == 2) return;
+    if (WHAT == 2)
+    {
+        rh.flush();
+        __syncthreads();
+        for (uint32_t i = threadIdx.x; i < npass * 256; i += EW_THREADS)
+            if (sh[i]) atomicAdd(&ghist[(uint64_t) b * RS_GHIST_STRIDE + i], sh[i]);
+        return;
+    }
     if (m && j0 + m == p)  // the last group of the block ends at p
     {
         const uint32_t g = p - (uint32_t) run;
@@ -612,27 +650,19 @@ __global__ void __launch_bounds__(EW_THREADS)
     }
 }
 
-// doubling round, step 1: keys/vals in current-order traversal. The tile is the radix sort's tile, so the
-// digit histogram of the first pass (low 8 bits of the key) is produced here and that pass skips its
-// own histogram kernel.
+// doubling round, step 1: (key, value) = (rank[SA[j] - h], SA[j] - h) in current-order traversal. (Fusing this gather into
+// the first sort pass was measured: the sort kernel runs at half occupancy and exposes the gather latency -- 3.9 ms
+// against 1.35 + 1.1 ms per 2^28 elements for the two kernels.)
 __global__ void __launch_bounds__(EW_THREADS)
     bwt_dbl_prepare_kernel(const uint32_t* __restrict__ sa, const uint32_t* __restrict__ rank, uint32_t h, uint64_t stride,
                            const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip, uint32_t* __restrict__ keys,
-                           uint32_t* __restrict__ vals, uint32_t tiles, uint32_t* __restrict__ hist)
+                           uint32_t* __restrict__ vals)
 {
-    __shared__ uint32_t sh[256];
-    const uint32_t      b = blockIdx.y;
+    const uint32_t b = blockIdx.y;
     if (skip[b]) return;
     const uint32_t p     = period[b];
     const uint32_t tile0 = blockIdx.x * EW_TILE;
-    uint32_t*      hout  = hist + ((uint64_t) b * 256) * tiles + blockIdx.x;
-    if (tile0 >= p)
-    {
-        hout[(uint64_t) threadIdx.x * tiles] = 0;
-        return;
-    }
-    sh[threadIdx.x] = 0;
-    __syncthreads();
+    if (tile0 >= p) return;
     const uint64_t base = (uint64_t) b * stride;
     const uint32_t tend = min(p, tile0 + EW_TILE);
     const uint32_t hm   = h % p;
@@ -640,13 +670,9 @@ __global__ void __launch_bounds__(EW_THREADS)
     {
         const uint32_t s = sa[base + j];
         const uint32_t v = s >= hm ? s - hm : s + p - hm;
-        const uint32_t k = rank[base + v];
         vals[base + j]   = v;
-        keys[base + j]   = k;
-        atomicAdd(&sh[k & 0xFFu], 1u);
+        keys[base + j]   = rank[base + v];
     }
-    __syncthreads();
-    hout[(uint64_t) threadIdx.x * tiles] = sh[threadIdx.x];
 }
 
 // 4. last column + primary index
@@ -756,12 +782,12 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     BRA_CUDA_TRY(cudaMemsetAsync(a.d_done, 0, nblk, st));
     BRA_CUDA_TRY(cudaMemsetAsync(a.d_ngroups, 0, nblk * 4, st));
 
-    // ---- 4-byte radix sort
+    // ---- radix sort on the first 4 symbols
     uint32_t *kA = a.d_keyA, *kB = a.d_keyB, *vA = a.d_valA, *vB = a.d_valB;
-    // diagnostic switches (parity triage): each turns one optional optimisation off
-    const bool no_alpha = getenv("BRA_B200_NO_ALPHA") != nullptr, no_dense = getenv("BRA_B200_NO_DENSE") != nullptr,
-               no_finish = getenv("BRA_B200_NO_FINISH") != nullptr;
-    uint32_t cbits = 8;
+    // parity triage switches (tools/fuzz_probe.py): each turns one optional optimisation off. Read once per process.
+    static const uint32_t diag = (getenv("BRA_B200_NO_ALPHA") ? 1u : 0u) | (getenv("BRA_B200_NO_DENSE") ? 2u : 0u) | (getenv("BRA_B200_NO_FINISH") ? 4u : 0u);
+    const bool            no_alpha = diag & 1u, no_dense = diag & 2u, no_finish = diag & 4u;
+    uint32_t   cbits = 8;
     if (a.d_alpha && !no_alpha)
     {
         BRA_CUDA_TRY(cudaMemsetAsync(a.d_alpha, 0, (size_t) nblk * 256, st));
@@ -781,11 +807,14 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         }
         if (cbits < 1 || cbits > 8) cbits = 8;
     }
-    BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, no_alpha ? nullptr : a.d_alpha, cbits, kA, tiles, a.d_hist));
-    for (uint32_t shift = 0; shift < 4 * cbits; shift += 8)
+    const size_t   ghist_bytes = (size_t) nblk * RS_GHIST_STRIDE * sizeof(uint32_t);
+    const uint32_t init_passes = (4 * cbits + 7) / 8;
+    BRA_CUDA_TRY(cudaMemsetAsync(a.d_hist, 0, ghist_bytes, st));
+    BRA_LAUNCH(P_BWT_KEYS, st, bwt_init_keys_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, no_alpha ? nullptr : a.d_alpha, cbits, kA, init_passes, a.d_hist));
+    for (uint32_t pass = 0; pass < init_passes; ++pass)
     {
         // the first pass takes the rotation indices as implicit values
-        if (!radix_pass_u32(kA, shift == 0 ? nullptr : vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, shift, 8, /*hist_ready=*/shift == 0, a.d_hist, st)) return false;
+        if (!radix_pass_u32(kA, pass == 0 ? nullptr : vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, pass, a.d_hist, st)) return false;
         std::swap(kA, kB);
         std::swap(vA, vB);
     }
@@ -797,9 +826,8 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<0><<<grid, EW_THREADS, 0, st>>>(kA, vA, nullptr, 0, a.stride, a.d_period, a.d_done, nullptr, fcur, a.d_tile_last, tiles,
                                                       a.d_ngroups, a.d_tile_heads));
     BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fcur, nullptr, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
-                                                                             a.d_maxgroup, a.d_sumsq, a.d_ngroups));
+                                                                             a.d_maxgroup, a.d_sumsq, a.d_ngroups, 0, nullptr));
     // the ranks themselves are written when (and for the blocks that) a doubling round follows
-    bool           ranks_pending = true;
     const uint8_t* ranks_old     = nullptr;
 
     uint32_t h = 4, rounds = 0, finishes = 0;
@@ -834,11 +862,10 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             BRA_LAUNCH(P_BWT_FINISH, st, bwt_finish_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, a.d_finskip, h, vA, fcur, vB, fnext,
                                                                                      a.d_tile_last, tiles, a.d_ngroups));
             BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vB, fnext, fcur, a.stride, a.d_period, a.d_finskip, a.d_tile_last, tiles, rk,
-                                                                                  a.d_maxgroup, a.d_sumsq, a.d_ngroups));
+                                                                                  a.d_maxgroup, a.d_sumsq, a.d_ngroups, 0, nullptr));
             BRA_LAUNCH(P_BWT_FINISH, st, bwt_copyback_kernel<<<grid, EW_THREADS, 0, st>>>(a.stride, a.d_period, a.d_finskip, vB, vA, fnext, fcur));
             // A block the finisher could not complete (rotations equal beyond its depth) goes on doubling: it needs every
             // rank written, its slots were reordered. The pending rank pass therefore stops trusting the older flags.
-            ranks_pending = true;
             ranks_old     = nullptr;
             ++finishes;
             continue;
@@ -854,35 +881,31 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         uint32_t dense_bits = 1;
         while ((1ull << dense_bits) < stat[2]) ++dense_bits;
         const bool dense = !no_dense && finishes == 0 && a.d_tile_heads != nullptr && (dense_bits + 7) / 8 < (key_bits + 7) / 8;
-        uint32_t   round_bits = key_bits;
+        const uint32_t round_bits = dense ? dense_bits : key_bits, round_passes = (round_bits + 7) / 8;
+        // the kernel that assigns the ranks also counts their digits for every pass of the round's sort
+        BRA_CUDA_TRY(cudaMemsetAsync(a.d_hist, 0, ghist_bytes, st));
         if (dense)
-        {
-            round_bits = dense_bits;
-            BRA_LAUNCH(P_BWT_RANKS, st, bwt_dense_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fcur, a.stride, a.d_period, a.d_done, a.d_tile_heads, tiles, rk, a.d_ngroups));
-            ranks_pending = false;
-        }
-        if (ranks_pending)
-        {
-            BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<2><<<grid, EW_THREADS, 0, st>>>(vA, fcur, ranks_old, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
-                                                                                     a.d_maxgroup, a.d_sumsq, a.d_ngroups));
-            ranks_pending = false;
-        }
+            BRA_LAUNCH(P_BWT_RANKS, st, bwt_dense_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fcur, a.stride, a.d_period, a.d_done, a.d_tile_heads, tiles, rk, a.d_ngroups,
+                                                                                        round_passes, a.d_hist));
+        else
+            // (every slot is visited for the histogram; ranks that are known to be in place already are not rewritten)
+            BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<2><<<grid, EW_THREADS, 0, st>>>(vA, fcur, ranks_old, a.stride, a.d_period, a.d_done,
+                                                                                     a.d_tile_last, tiles, rk, a.d_maxgroup, a.d_sumsq, a.d_ngroups, round_passes, a.d_hist));
         BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_done, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
-        BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, h, a.stride, a.d_period, a.d_done, kB, vB, tiles, a.d_hist));
+        BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, h, a.stride, a.d_period, a.d_done, kB, vB));
         std::swap(kA, kB);
         std::swap(vA, vB);
-        for (uint32_t shift = 0; shift < round_bits; shift += 8)
+        for (uint32_t pass = 0; pass < round_passes; ++pass)
         {
-            if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, shift, 8, /*hist_ready=*/shift == 0, a.d_hist, st)) return false;
+            if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, pass, a.d_hist, st)) return false;
             std::swap(kA, kB);
             std::swap(vA, vB);
         }
         BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(nullptr, vA, rk, h, a.stride, a.d_period, a.d_done, fcur, fnext, a.d_tile_last, tiles,
                                                           a.d_ngroups, a.d_tile_heads));
         BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
-                                                                                 a.d_maxgroup, a.d_sumsq, a.d_ngroups));
+                                                                                 a.d_maxgroup, a.d_sumsq, a.d_ngroups, 0, nullptr));
         std::swap(fcur, fnext);
-        ranks_pending = true;
         ranks_old     = dense ? nullptr : fnext;  // the flags of before this round; after a round on group numbers every rank is rewritten
         h *= 2;
         ++rounds;
