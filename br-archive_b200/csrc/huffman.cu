@@ -200,6 +200,27 @@ __global__ void __launch_bounds__(HF_THREADS)
     const uint32_t gbit0 = t_bitoff[(uint64_t) b * tiles + t];  // first bit of the tile in the block's stream
     const uint32_t skew  = gbit0 & 31u;                         // image word 0 == global word gbit0/32
     off += skew;
+    // The first word of the tile also holds the last `skew` bits of the codes before the tile: thread 0 walks back
+    // over those symbols (at most 32 of them) and puts their bits too, so that this CTA owns the whole word and stores
+    // it plainly. The word the tile ends in belongs to the next tile in the same way.
+    if (threadIdx.x == 0 && skew)
+    {
+        uint32_t pos = skew;  // bits of the word still to be covered, counted from the word start
+        for (uint32_t j = tile0; j > 0 && pos > 0;)
+        {
+            --j;
+            uint32_t l    = slen[p[j]];
+            uint64_t code = scode[p[j]];
+            if (l == 0) continue;
+            if (l > pos)  // the code starts in the previous word: keep its last `pos` bits
+            {
+                code &= (1ull << pos) - 1ull;
+                l = pos;
+            }
+            pos -= l;
+            huf_put(img, pos, code, l);
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 16; ++i)
     {
@@ -210,18 +231,11 @@ __global__ void __launch_bounds__(HF_THREADS)
     }
     __syncthreads();
 
-    const uint32_t nwords = (skew + tile_bits + 31u) >> 5;
-    uint32_t*      ow     = reinterpret_cast<uint32_t*>(out + (uint64_t) b * out_stride) + (gbit0 >> 5);
+    const uint32_t nwords    = (skew + tile_bits + 31u) >> 5;
+    const bool     owns_last = ((skew + tile_bits) & 31u) == 0 || tile0 + HF_TILE >= r;  // ends on a word boundary, or nothing follows
+    uint32_t*      ow        = reinterpret_cast<uint32_t*>(out + (uint64_t) b * out_stride) + (gbit0 >> 5);
     for (uint32_t i = threadIdx.x; i < nwords; i += HF_THREADS)
-    {
-        const uint32_t v = __byte_perm(img[i], 0, 0x0123);  // big-endian image -> little-endian store
-        if (i == 0 || i + 1 == nwords)
-        {
-            if (v) atomicOr(&ow[i], v);  // word shared with the neighbouring tile
-        }
-        else
-            ow[i] = v;
-    }
+        if (i + 1 < nwords || owns_last) ow[i] = __byte_perm(img[i], 0, 0x0123);  // big-endian image -> little-endian store
 }
 
 bool huf_encode_batch(const HufEncArgs& a, cudaStream_t st)
@@ -237,7 +251,6 @@ bool huf_encode_batch(const HufEncArgs& a, cudaStream_t st)
     BRA_LAUNCH(P_HUF_BUILD, st, huf_build_kernel<<<a.nblk, 32, 0, st>>>(a.d_hist, a.d_rlen, a.d_hdr, a.d_codes, a.d_ok));
     BRA_LAUNCH(P_HUF_BITS, st, huf_tile_bits_kernel<<<grid, HF_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, a.d_hdr, tiles, a.d_t_bits));
     BRA_LAUNCH(P_HUF_BITS, st, huf_scan_bits_kernel<<<a.nblk, 256, 0, st>>>(a.d_t_bits, a.d_rlen, tiles, a.d_hdr, a.d_clen));
-    BRA_CUDA_TRY(cudaMemsetAsync(a.d_out, 0, (size_t) a.nblk * a.out_stride, st));
     BRA_LAUNCH(P_HUF_PACK, st, huf_pack_kernel<<<grid, HF_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, a.d_hdr, a.d_codes, tiles, a.d_t_bits, a.d_out, a.out_stride));
     BRA_CUDA_TRY(cudaGetLastError());
     return true;
