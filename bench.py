@@ -178,6 +178,32 @@ ALG_PER_ELEM = {"radix_scatter": 16, "radix_scatter_implicit": 12, "radix_hist":
                 "bwt_prepare": 16, "bwt_finish": 10, "bwt_gather": 6, "crc32c": 1, "ibwt_walk_len": 4, "ibwt_walk_emit": 5}
 
 
+
+def bind_near_gpu(torch, local_rank):
+    """Run this rank (and therefore allocate its pinned host buffers: first touch) on the CPUs of the NUMA node its GPU
+    hangs off, when the box says which one that is and this process may run there. Returns what was done, for the record."""
+    info = {"numa_node": None, "bound": False}
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{str(bdf).lower()}/numa_node").read())
+        info["numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+            info["cpus"] = len(allowed)
+    except (OSError, ValueError, AttributeError):
+        pass
+    return info
+
+
 # ------------------------------------------------------------------------------------------ one shape on this rank's GPU
 def run_shape(pkg, torch, dist, kind, block, nbytes, batch, steps, warmup, e2e_steps, rank, world, local_rank, peak, parity_blocks, clocks=False):
     """Device-resident timing (CUDA events on the launching stream, max over ranks), parity sample of the timed output,
@@ -484,6 +510,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the compression path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_near_gpu(torch, local_rank) if world > 1 else {"numa_node": None, "bound": False}
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -518,7 +545,7 @@ def main():
         h["roofline"]["peak_source"] = peak_src
         line = {"metric": METRIC, "value": h["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-                "data": "synthetic", "config": config}
+                "data": "synthetic", "config": config, "host_placement": numa}
         for k in ("encode_gbs", "decode_gbs", "compressed_ratio", "rle_ratio", "bwt_doubling_rounds", "huffman_sync_sweeps", "clocks", "e2e", "gpu_launches",
                   "kernel_ms", "roofline", "chain_roofline", "parity_sample"):
             line[k] = h[k]

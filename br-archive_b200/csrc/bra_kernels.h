@@ -186,11 +186,13 @@ struct HufDecArgs
     uint16_t*       d_sub_count;   // nblk*seqs*256
     uint32_t *      d_seq_entry, *d_seq_exit, *d_seq_count;  // nblk*seqs
     uint32_t *      d_end_bit, *d_changed;
+    uint8_t*        d_phase;       // optional, nblk*seqs*huf_dec_phase_bytes_per_seq(): enables the phase mode of the synchronisation
     uint32_t*       h_sweeps;
     uint32_t*       h_mail;  // optional pinned, device-visible host word for the sweep status (see BwtFwdArgs::h_mail)
 };
 bool     huf_decode_batch(const HufDecArgs& a, cudaStream_t st);
 uint32_t huf_dec_seqs(uint32_t max_c);
 uint32_t huf_dec_subs_per_seq();
+uint32_t huf_dec_phase_bytes_per_seq();
 
 }  // namespace bra

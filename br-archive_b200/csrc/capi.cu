@@ -515,6 +515,7 @@ extern "C" uint8_t* bra_huffman_decode(const bra_huffman_t* meta, const uint8_t*
     const uint64_t o_pay = B.take<uint8_t>(PS), o_hdr = B.take<uint8_t>(272), o_out = B.take<uint8_t>(RS), o_tab = B.take<bra_huf_dec_t>(1);
     const uint64_t o_ss = B.take<uint8_t>(seqs * huf_dec_subs_per_seq()), o_sc = B.take<uint16_t>(seqs * huf_dec_subs_per_seq());
     const uint64_t o_se = B.take<uint32_t>(seqs), o_sx = B.take<uint32_t>(seqs), o_sn = B.take<uint32_t>(seqs), o_small = B.take<uint32_t>(8);
+    const uint64_t o_ph = B.take<uint8_t>((uint64_t) seqs * huf_dec_phase_bytes_per_seq());
     if (!scratch(B.used)) return nullptr;
     uint8_t hdr[268];
     memset(hdr, 0, 4);
@@ -529,7 +530,7 @@ extern "C" uint8_t* bra_huffman_decode(const bra_huffman_t* meta, const uint8_t*
     a.d_pay = at<uint8_t>(o_pay); a.pay_stride = PS; a.d_clen = sm; a.d_hdr = at<uint8_t>(o_hdr); a.max_c = c; a.nblk = 1; a.d_out = at<uint8_t>(o_out);
     a.out_stride = RS; a.d_tabs = at<bra_huf_dec_t>(o_tab); a.d_err = sm + 1; a.d_sub_start = at<uint8_t>(o_ss); a.d_sub_count = at<uint16_t>(o_sc);
     a.d_seq_entry = at<uint32_t>(o_se); a.d_seq_exit = at<uint32_t>(o_sx); a.d_seq_count = at<uint32_t>(o_sn); a.d_end_bit = sm + 2;
-    a.d_changed = sm + 3;
+    a.d_changed = sm + 3; a.d_phase = at<uint8_t>(o_ph);
     if (!huf_decode_batch(a, g_st)) return nullptr;
     uint32_t err = 1;
     if (cudaMemcpyAsync(&err, sm + 1, 4, cudaMemcpyDeviceToHost, g_st) != cudaSuccess || !sync_ok()) return nullptr;

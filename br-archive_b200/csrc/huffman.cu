@@ -294,6 +294,20 @@ struct HdShared
     uint32_t      red[34];
 };
 
+// Phase mode of the synchronisation (codes of at most HD_PHASE_MAX bits): a code that crosses a subsequence border ends
+// fewer than max_len bits behind it, so a subsequence has at most max_len possible starts ("phases"). Every subsequence
+// is walked once from each of them, which gives the map start -> (start of the next subsequence, codewords inside); the
+// true starts then follow by chaining the maps from the entry of the sequence -- in a time that does not depend on how
+// fast the code re-synchronises (near-uniform code lengths, i.e. incompressible data, hardly ever do).
+#define HD_PHASE_MAX 12u
+#define HD_PHASE_SEQ_BYTES (HD_PHASE_MAX * HD_THREADS * 3u + 16u)  // per sequence: exits u8 [phase][sub], counts u16 [phase][sub], exit map of the sequence
+struct HdSyncShared
+{
+    HdShared S;
+    uint16_t pc[HD_PHASE_MAX][HD_THREADS];
+    uint8_t  pe[HD_PHASE_MAX][HD_THREADS];
+};
+
 // Thread k streams through words 32k..32k+31: unswizzled, all 256 threads would sit on one bank.
 // Word i lives at (i & ~31) | ((i ^ (i >> 5)) & 31), so that threads at the same column hit 32 banks.
 __device__ __forceinline__ uint32_t hd_word(const HdShared& S, uint32_t i) { return S.words[(i & ~31u) | ((i ^ (i >> 5)) & 31u)]; }
@@ -401,10 +415,12 @@ __global__ void __launch_bounds__(HD_THREADS)
     huf_dec_sync_kernel(const uint8_t* __restrict__ pay, uint64_t pay_stride, const uint32_t* __restrict__ clen, const bra_huf_dec_t* __restrict__ tabs,
                         const uint32_t* __restrict__ err, uint32_t seqs, uint8_t* __restrict__ sub_start, uint16_t* __restrict__ sub_count,
                         uint32_t* __restrict__ seq_entry, uint32_t* __restrict__ seq_exit, uint32_t* __restrict__ seq_count,
-                        uint32_t* __restrict__ changed_flag)
+                        uint32_t* __restrict__ changed_flag, uint8_t* __restrict__ phase_ws)
 {
-    __shared__ HdShared S;
-    const uint32_t      b = blockIdx.y, seq = blockIdx.x;
+    extern __shared__ __align__(16) uint8_t hd_sync_smem[];
+    HdSyncShared&  SS = *reinterpret_cast<HdSyncShared*>(hd_sync_smem);
+    HdShared&      S  = SS.S;
+    const uint32_t b = blockIdx.y, seq = blockIdx.x;
     const uint32_t      c = clen[b];
     if ((uint64_t) seq * HD_SEQ_BYTES >= c || err[b]) return;
     const uint64_t sidx = (uint64_t) b * seqs + seq;
@@ -428,6 +444,56 @@ __global__ void __launch_bounds__(HD_THREADS)
     const uint64_t sub_idx  = sidx * HD_THREADS + k;
     const uint32_t data_end = min((uint32_t) HD_SEQ_BITS + 64u, (c - seq * HD_SEQ_BYTES) * 8u);  // relative bit where the payload ends
     __syncthreads();
+    const uint32_t L = S.tab.max_len;
+    if (phase_ws && L >= 1 && L <= HD_PHASE_MAX && entry < L)
+    {
+        uint8_t*  g_pe  = phase_ws + sidx * HD_PHASE_SEQ_BYTES;
+        uint16_t* g_pc  = reinterpret_cast<uint16_t*>(g_pe + HD_PHASE_MAX * HD_THREADS);
+        uint8_t*  g_map = g_pe + HD_PHASE_MAX * HD_THREADS * 3u;
+        if (first_run)
+        {
+            hd_build_lut(S);
+            __syncthreads();
+            for (uint32_t o = 0; o < L; ++o)
+            {
+                uint32_t cnt;
+                bool     dead;
+                uint32_t nx = hd_walk(S, k * HD_SUB_BITS + o, (k + 1) * HD_SUB_BITS, data_end, &cnt, &dead);
+                uint32_t ex = (dead || nx < (k + 1) * HD_SUB_BITS) ? 0u : nx - (k + 1) * HD_SUB_BITS;  // dead path / payload ended: neutral
+                if (ex >= L) ex = 0;
+                SS.pe[o][k] = (uint8_t) ex;
+                SS.pc[o][k] = (uint16_t) cnt;
+                g_pe[o * HD_THREADS + k] = (uint8_t) ex;
+                g_pc[o * HD_THREADS + k] = (uint16_t) cnt;
+            }
+        }
+        else
+            for (uint32_t o = 0; o < L; ++o)
+            {
+                SS.pe[o][k] = g_pe[o * HD_THREADS + k];
+                SS.pc[o][k] = g_pc[o * HD_THREADS + k];
+            }
+        __syncthreads();
+        if (k < L)  // thread o chains the maps from entry phase o; the one that starts from the true entry records the path
+        {
+            const bool mine = k == entry;
+            uint32_t   ph   = k;
+            for (uint32_t j = 0; j < HD_THREADS; ++j)
+            {
+                if (mine)
+                {
+                    S.start[j] = j * HD_SUB_BITS + ph;
+                    S.count[j] = SS.pc[ph][j];
+                }
+                ph = SS.pe[ph][j];
+            }
+            if (first_run) g_map[k] = (uint8_t) ph;
+            if (mine) S.start[HD_THREADS] = HD_SEQ_BITS + ph;
+        }
+        __syncthreads();
+    }
+    else
+    {
     hd_build_lut(S);
     __syncthreads();
     // current guess for this subsequence's first codeword. First run: decode a short warm-up
@@ -498,6 +564,7 @@ __global__ void __launch_bounds__(HD_THREADS)
         if (k < nact) S.start[j + 1] = nx;
         __syncthreads();
     }
+    }
     const uint32_t mycount = S.count[k];
     sub_start[sub_idx] = (uint8_t) (S.start[k] - k * HD_SUB_BITS);
     sub_count[sub_idx] = (uint16_t) mycount;
@@ -513,6 +580,24 @@ __global__ void __launch_bounds__(HD_THREADS)
             seq_exit[sidx] = ex;
             atomicAdd(changed_flag, 1u);
         }
+    }
+}
+
+// Phase mode: the true entry of every sequence of a block, by chaining the sequences' exit maps (one thread per block).
+__global__ void huf_dec_phase_chain_kernel(const uint32_t* __restrict__ clen, const bra_huf_dec_t* __restrict__ tabs, const uint32_t* __restrict__ err,
+                                           uint32_t seqs, const uint8_t* __restrict__ phase_ws, uint32_t* __restrict__ seq_exit, uint32_t nblk)
+{
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nblk || err[b]) return;
+    const uint32_t L = tabs[b].max_len;
+    if (L < 1 || L > HD_PHASE_MAX) return;
+    const uint32_t nseq = (clen[b] + HD_SEQ_BYTES - 1) / HD_SEQ_BYTES;
+    uint32_t       ph   = 0;
+    for (uint32_t s = 0; s < nseq; ++s)
+    {
+        const uint64_t sidx = (uint64_t) b * seqs + s;
+        ph                  = phase_ws[sidx * HD_PHASE_SEQ_BYTES + HD_PHASE_MAX * HD_THREADS * 3u + ph];
+        seq_exit[sidx]      = ph;
     }
 }
 
@@ -678,14 +763,23 @@ bool huf_decode_batch(const HufDecArgs& a, cudaStream_t st)
     BRA_CUDA_TRY(cudaMemsetAsync(a.d_seq_entry, 0xFF, (size_t) a.nblk * seqs * 4, st));
     BRA_CUDA_TRY(cudaMemsetAsync(a.d_seq_exit, 0, (size_t) a.nblk * seqs * 4, st));  // first guess: codewords start on sequence boundaries
     BRA_CUDA_TRY(cudaMemsetAsync(a.d_end_bit, 0, (size_t) a.nblk * 4, st));
-    uint32_t sweeps = 0;
+    uint32_t     sweeps    = 0;
+    const size_t sync_smem = sizeof(HdSyncShared);
+    BRA_CUDA_TRY(cudaFuncSetAttribute(huf_dec_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sync_smem));
+    auto sweep = [&]() -> bool {
+        BRA_LAUNCH(P_HUF_DEC_SYNC, st, huf_dec_sync_kernel<<<grid, HD_THREADS, sync_smem, st>>>(a.d_pay, a.pay_stride, a.d_clen, a.d_tabs, a.d_err, seqs, a.d_sub_start,
+                                                         a.d_sub_count, a.d_seq_entry, a.d_seq_exit, a.d_seq_count, a.d_changed, a.d_phase));
+        ++sweeps;
+        return true;
+    };
     for (;;)
     {
         BRA_CUDA_TRY(cudaMemsetAsync(a.d_changed, 0, 4, st));
-        for (int rep = 0; rep < 2; ++rep)
-            BRA_LAUNCH(P_HUF_DEC_SYNC, st, huf_dec_sync_kernel<<<grid, HD_THREADS, 0, st>>>(a.d_pay, a.pay_stride, a.d_clen, a.d_tabs, a.d_err, seqs, a.d_sub_start,
-                                                             a.d_sub_count, a.d_seq_entry, a.d_seq_exit, a.d_seq_count, a.d_changed));
-        sweeps += 2;
+        if (!sweep()) return false;
+        if (sweeps == 1 && a.d_phase)
+            // blocks in phase mode: every sequence knows its exit for every entry now -- settle the entries in one go
+            BRA_LAUNCH(P_HUF_DEC_SCAN, st, huf_dec_phase_chain_kernel<<<bra_div_up(a.nblk, 64), 64, 0, st>>>(a.d_clen, a.d_tabs, a.d_err, seqs, a.d_phase, a.d_seq_exit, a.nblk));
+        if (!sweep()) return false;
         uint32_t changed = 0;
         if (!read_changed(a, st, &changed)) return false;
         // the first pair of sweeps always reports changes (every CTA publishes its first exit)
@@ -694,9 +788,7 @@ bool huf_decode_batch(const HufDecArgs& a, cudaStream_t st)
         {
             // cheap confirmation sweep: if nothing moves any more we are at the fixed point
             BRA_CUDA_TRY(cudaMemsetAsync(a.d_changed, 0, 4, st));
-            BRA_LAUNCH(P_HUF_DEC_SYNC, st, huf_dec_sync_kernel<<<grid, HD_THREADS, 0, st>>>(a.d_pay, a.pay_stride, a.d_clen, a.d_tabs, a.d_err, seqs, a.d_sub_start,
-                                                             a.d_sub_count, a.d_seq_entry, a.d_seq_exit, a.d_seq_count, a.d_changed));
-            ++sweeps;
+            if (!sweep()) return false;
             if (!read_changed(a, st, &changed)) return false;
             if (changed == 0) break;
         }
@@ -713,5 +805,6 @@ bool huf_decode_batch(const HufDecArgs& a, cudaStream_t st)
 uint32_t huf_enc_tiles(uint32_t max_r) { return bra_div_up(max_r, HF_TILE); }
 uint32_t huf_dec_seqs(uint32_t max_c) { return bra_div_up(max_c, HD_SEQ_BYTES); }
 uint32_t huf_dec_subs_per_seq() { return HD_THREADS; }
+uint32_t huf_dec_phase_bytes_per_seq() { return HD_PHASE_SEQ_BYTES; }
 
 }  // namespace bra

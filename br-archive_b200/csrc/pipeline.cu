@@ -71,7 +71,7 @@ struct EncWs
 };
 struct DecWs
 {
-    uint8_t * R, *M, *L, *summ, *state, *sub_start, *t_exit, *t_entry, *wtmp;
+    uint8_t * R, *M, *L, *summ, *state, *sub_start, *t_exit, *t_entry, *wtmp, *phase;
     uint16_t* sub_count;
     uint32_t *W, *hist, *rlen, *clen, *nlen, *primary, *err, *seq_entry, *seq_exit, *seq_count, *end_bit, *changed, *t_tok, *t_ocnt, *woff,
         *orbit;
@@ -118,6 +118,7 @@ static void carve_dec(Arena& A, uint32_t S, uint32_t nb, DecWs& w)
     w.summ = A.take<uint8_t>(nb * segs * 256); w.state = A.take<uint8_t>(nb * segs * 256);
     const uint64_t seqs = huf_dec_seqs((uint32_t) PS);
     w.sub_start = A.take<uint8_t>(nb * seqs * huf_dec_subs_per_seq()); w.sub_count = A.take<uint16_t>(nb * seqs * huf_dec_subs_per_seq());
+    w.phase = A.take<uint8_t>(nb * seqs * huf_dec_phase_bytes_per_seq());
     w.seq_entry = A.take<uint32_t>(nb * seqs); w.seq_exit = A.take<uint32_t>(nb * seqs); w.seq_count = A.take<uint32_t>(nb * seqs);
     const uint64_t rt = rle_dec_tiles((uint32_t) RS);
     w.t_exit = A.take<uint8_t>(nb * rt * rle_dec_entries()); w.t_entry = A.take<uint8_t>(nb * rt);
@@ -377,7 +378,7 @@ bool decode_batch(bra_b200_ctx* c, const uint8_t* d_hdr, const uint8_t* d_payloa
     ha.d_pay = d_payload; ha.pay_stride = c->pay_stride; ha.d_clen = w.clen; ha.d_hdr = d_hdr; ha.max_c = max_c; ha.nblk = nb;
     ha.d_out = w.R; ha.out_stride = c->rle_stride; ha.d_tabs = w.tabs; ha.d_err = w.err;
     ha.d_sub_start = w.sub_start; ha.d_sub_count = w.sub_count; ha.d_seq_entry = w.seq_entry; ha.d_seq_exit = w.seq_exit;
-    ha.d_seq_count = w.seq_count; ha.d_end_bit = w.end_bit; ha.d_changed = w.changed;
+    ha.d_seq_count = w.seq_count; ha.d_end_bit = w.end_bit; ha.d_changed = w.changed; ha.d_phase = w.phase;
     uint32_t sweeps = 0;
     ha.h_sweeps = &sweeps;
     ha.h_mail   = mail_huffman(c);
