@@ -49,9 +49,10 @@ size_t radix_hist_bytes(uint32_t max_len, uint32_t nblk);
 // a few bytes would wait on its copy engine behind the bulk copies of the neighbouring pipeline stages
 bool mail_fetch(uint32_t* d_dst, const uint32_t* h_src, uint32_t words, cudaStream_t st);
 bool mail_publish(uint32_t* h_dst, const uint32_t* d_src, uint32_t words, cudaStream_t st);
-// vals == nullptr: the values are the element indices (first pass of a sort)
+// vals == nullptr: the values are the element indices (first pass of a sort). The sort key starts at bit `key_shift` of
+// the key word; pass p looks at its bits [8p, 8p+8).
 bool radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t stride, const uint32_t* d_len,
-                    const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t pass, uint32_t* d_hist, cudaStream_t st);
+                    const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t pass, uint32_t key_shift, uint32_t* d_hist, cudaStream_t st);
 // u8 keys, implicit index values, output word (index << 8) | key; computes its own histogram
 bool radix_pass_u8_index_packed(const uint8_t* keys, uint32_t* packed_out, uint64_t stride, const uint32_t* d_len, uint32_t max_len,
                                 uint32_t nblk, uint32_t* d_hist, cudaStream_t st);

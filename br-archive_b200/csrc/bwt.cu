@@ -675,6 +675,164 @@ __global__ void __launch_bounds__(EW_THREADS)
     }
 }
 
+// ---- packed rounds (blocks of at most 2^21 bytes) -----------------------------------------------------------------------
+// A doubling round orders element v = SA[j] - h by (group of v, group of v + h). The second component is the group of
+// traversal slot j itself, i.e. the position of the last head at or before j -- known while the round's records are
+// written, no gather needed. With 21 bits per field the triple (key, second key, v) fits the 8 bytes per element the sort
+// moves anyway: hi = key << 11 | second >> 10, lo = (second & 1023) << 22 | v. After the sort, new heads are where
+// (key, second) differs from the left neighbour: a streaming pass instead of one more random gather per element.
+#define BWT_PACK_MAX_N (1u << 21)
+#define BWT_PACK_KEY_SHIFT 11u
+
+// Both kernels are warp-striped: warp w owns slots [512 w, 512 w + 512) of the tile and visits them in 16 rounds of 32
+// consecutive slots, so every load and store is one contiguous 128-byte (or 32-byte) piece per warp, and "last head at
+// or before slot j" is a ballot and a count-leading-zeros away.
+__global__ void __launch_bounds__(EW_THREADS, 4)
+    bwt_dbl_prepare_packed_kernel(const uint32_t* __restrict__ sa, const uint32_t* __restrict__ rank, const uint8_t* __restrict__ flags, uint32_t h,
+                                  uint64_t stride, const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip,
+                                  const int* __restrict__ tile_last, uint32_t tiles, uint32_t* __restrict__ hi_out, uint32_t* __restrict__ lo_out)
+{
+    __shared__ int red[8], s_wl[8];
+    const uint32_t b = blockIdx.y;
+    if (skip[b]) return;
+    const uint32_t p     = period[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= p) return;
+    const uint64_t base = (uint64_t) b * stride;
+    const uint32_t hm   = h % p;
+    const uint32_t w = warp_id(), l = lane_id();
+    const uint32_t seg0 = tile0 + w * 512;
+    // last head of the warp's slots: one ballot per round
+    int wl = -1;
+#pragma unroll 4
+    for (int r = 0; r < 16; ++r)
+    {
+        const uint32_t j  = seg0 + r * 32 + l;
+        const uint32_t hb = __ballot_sync(BRA_FULL, j < p && flags[base + j] != 0);
+        if (hb) wl = (int) (seg0 + r * 32 + (31 - __clz(hb)));
+    }
+    // carry-in: last head before this tile, then before this warp's slots
+    int carry = 0;
+    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += EW_THREADS) carry = max(carry, tile_last[(uint64_t) b * tiles + t]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) carry = max(carry, __shfl_xor_sync(BRA_FULL, carry, d));
+    if (l == 0)
+    {
+        red[w]  = carry;
+        s_wl[w] = wl;
+    }
+    __syncthreads();
+    int run = red[0];
+    for (int i = 1; i < 8; ++i) run = max(run, red[i]);
+    for (uint32_t i = 0; i < w; ++i) run = max(run, s_wl[i]);
+    // two halves of eight rounds: eight independent gathers per lane in flight, registers for four CTAs per SM
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half)
+    {
+        uint32_t v[8], k[8];
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+        {
+            const uint32_t j = seg0 + (half * 8 + r) * 32 + l;
+            const uint32_t s = j < p ? sa[base + j] : hm;
+            v[r]             = s >= hm ? s - hm : s + p - hm;
+        }
+#pragma unroll
+        for (int r = 0; r < 8; ++r) k[r] = seg0 + (half * 8 + r) * 32 + l < p ? rank[base + v[r]] : 0u;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+        {
+            const uint32_t j0r  = seg0 + (half * 8 + r) * 32;
+            const uint32_t j    = j0r + l;
+            const uint32_t hb   = __ballot_sync(BRA_FULL, j < p && flags[base + j] != 0);
+            const uint32_t mine = hb & (lanemask_lt() | (1u << l));
+            const uint32_t r2   = mine ? j0r + (31 - __clz(mine)) : (uint32_t) run;
+            if (hb) run = (int) (j0r + (31 - __clz(hb)));
+            if (j < p)
+            {
+                hi_out[base + j] = (k[r] << BWT_PACK_KEY_SHIFT) | (r2 >> 10);
+                lo_out[base + j] = ((r2 & 1023u) << 22) | v[r];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+    bwt_heads_packed_kernel(const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo, uint64_t stride, const uint32_t* __restrict__ period,
+                            const uint8_t* __restrict__ skip, uint8_t* __restrict__ flags, uint32_t* __restrict__ sa_out, int* __restrict__ tile_last,
+                            uint32_t tiles, uint32_t* __restrict__ ngroups, uint32_t* __restrict__ tile_heads)
+{
+    __shared__ int      s_last[8];
+    __shared__ uint32_t s_cnt[8];
+    const uint32_t      b = blockIdx.y;
+    if (skip[b]) return;
+    const uint32_t p     = period[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= p) return;
+    const uint64_t base = (uint64_t) b * stride;
+    const uint32_t w = warp_id(), l = lane_id();
+    const uint32_t seg0 = tile0 + w * 512;
+    int            last = -1;
+    uint32_t       cnt  = 0;
+    uint32_t       xh[16], xl[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+    {
+        const uint32_t j = seg0 + r * 32 + l;
+        xh[r]            = j < p ? hi[base + j] : 0u;
+        xl[r]            = j < p ? lo[base + j] : 0u;
+    }
+    // the element left of the warp's first slot
+    uint32_t ph = 0, pl = 0;
+    if (seg0 > 0 && seg0 < p)
+    {
+        ph = hi[base + seg0 - 1];
+        pl = lo[base + seg0 - 1] >> 22;
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r)
+    {
+        const uint32_t j  = seg0 + r * 32 + l;
+        const uint32_t s2 = xl[r] >> 22;
+        uint32_t       lh = __shfl_up_sync(BRA_FULL, xh[r], 1), ll = __shfl_up_sync(BRA_FULL, s2, 1);
+        if (l == 0)
+        {
+            lh = ph;
+            ll = pl;
+        }
+        const bool     head = j < p && (j == 0 || xh[r] != lh || s2 != ll);
+        const uint32_t hb   = __ballot_sync(BRA_FULL, head);
+        if (hb) last = (int) (seg0 + r * 32 + (31 - __clz(hb)));
+        cnt += __popc(hb);
+        if (j < p)
+        {
+            flags[base + j]  = head ? 1 : 0;
+            sa_out[base + j] = xl[r] & 0x3FFFFFu;
+        }
+        ph = __shfl_sync(BRA_FULL, xh[r], 31);
+        pl = __shfl_sync(BRA_FULL, s2, 31);
+    }
+    if (l == 0)
+    {
+        s_last[w] = last;
+        s_cnt[w]  = cnt;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        int      L = -1;
+        uint32_t c = 0;
+        for (int i = 0; i < 8; ++i)
+        {
+            L = max(L, s_last[i]);
+            c += s_cnt[i];
+        }
+        tile_last[(uint64_t) b * tiles + blockIdx.x] = L;
+        if (tile_heads) tile_heads[(uint64_t) b * tiles + blockIdx.x] = c;
+        atomicAdd(&ngroups[b], c);
+    }
+}
+
 // 4. last column + primary index
 __global__ void __launch_bounds__(EW_THREADS)
     bwt_gather_kernel(const uint8_t* __restrict__ in, const uint32_t* __restrict__ sa, uint64_t stride, const uint32_t* __restrict__ len,
@@ -814,7 +972,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     for (uint32_t pass = 0; pass < init_passes; ++pass)
     {
         // the first pass takes the rotation indices as implicit values
-        if (!radix_pass_u32(kA, pass == 0 ? nullptr : vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, pass, a.d_hist, st)) return false;
+        if (!radix_pass_u32(kA, pass == 0 ? nullptr : vA, kB, vB, a.stride, a.d_period, nullptr, max_n, nblk, pass, 0, a.d_hist, st)) return false;
         std::swap(kA, kB);
         std::swap(vA, vB);
     }
@@ -863,7 +1021,14 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
                                                                                      a.d_tile_last, tiles, a.d_ngroups));
             BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vB, fnext, fcur, a.stride, a.d_period, a.d_finskip, a.d_tile_last, tiles, rk,
                                                                                   a.d_maxgroup, a.d_sumsq, a.d_ngroups, 0, nullptr));
-            BRA_LAUNCH(P_BWT_FINISH, st, bwt_copyback_kernel<<<grid, EW_THREADS, 0, st>>>(a.stride, a.d_period, a.d_finskip, vB, vA, fnext, fcur));
+            if (stat[1] == stat[0])
+            {
+                // every block still sorting went through the finisher: its outputs simply become the current buffers
+                std::swap(vA, vB);
+                std::swap(fcur, fnext);
+            }
+            else
+                BRA_LAUNCH(P_BWT_FINISH, st, bwt_copyback_kernel<<<grid, EW_THREADS, 0, st>>>(a.stride, a.d_period, a.d_finskip, vB, vA, fnext, fcur));
             // A block the finisher could not complete (rotations equal beyond its depth) goes on doubling: it needs every
             // rank written, its slots were reordered. The pending rank pass therefore stops trusting the older flags.
             ranks_old     = nullptr;
@@ -892,17 +1057,36 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<2><<<grid, EW_THREADS, 0, st>>>(vA, fcur, ranks_old, a.stride, a.d_period, a.d_done,
                                                                                      a.d_tile_last, tiles, rk, a.d_maxgroup, a.d_sumsq, a.d_ngroups, round_passes, a.d_hist));
         BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_done, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
-        BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, h, a.stride, a.d_period, a.d_done, kB, vB));
-        std::swap(kA, kB);
-        std::swap(vA, vB);
-        for (uint32_t pass = 0; pass < round_passes; ++pass)
+        if (max_n <= BWT_PACK_MAX_N)
         {
-            if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, pass, a.d_hist, st)) return false;
+            // packed records: the second sort key travels with the element, the new heads need no gather
+            BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_packed_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, fcur, h, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, kB, vB));
             std::swap(kA, kB);
             std::swap(vA, vB);
+            for (uint32_t pass = 0; pass < round_passes; ++pass)
+            {
+                if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, pass, BWT_PACK_KEY_SHIFT, a.d_hist, st)) return false;
+                std::swap(kA, kB);
+                std::swap(vA, vB);
+            }
+            BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_packed_kernel<<<grid, EW_THREADS, 0, st>>>(kA, vA, a.stride, a.d_period, a.d_done, fnext, vB, a.d_tile_last, tiles, a.d_ngroups,
+                                                                                         a.d_tile_heads));
+            std::swap(vA, vB);  // the plain rotation indices
         }
-        BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(nullptr, vA, rk, h, a.stride, a.d_period, a.d_done, fcur, fnext, a.d_tile_last, tiles,
-                                                          a.d_ngroups, a.d_tile_heads));
+        else
+        {
+            BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, h, a.stride, a.d_period, a.d_done, kB, vB));
+            std::swap(kA, kB);
+            std::swap(vA, vB);
+            for (uint32_t pass = 0; pass < round_passes; ++pass)
+            {
+                if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, pass, 0, a.d_hist, st)) return false;
+                std::swap(kA, kB);
+                std::swap(vA, vB);
+            }
+            BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(nullptr, vA, rk, h, a.stride, a.d_period, a.d_done, fcur, fnext, a.d_tile_last, tiles,
+                                                              a.d_ngroups, a.d_tile_heads));
+        }
         BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
                                                                                  a.d_maxgroup, a.d_sumsq, a.d_ngroups, 0, nullptr));
         std::swap(fcur, fnext);

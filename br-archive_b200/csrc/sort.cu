@@ -427,10 +427,10 @@ static bool radix_launch(RsParams& P, uint32_t* d_hist, uint32_t pass, uint32_t 
 }
 
 bool radix_pass_u32(const uint32_t* keys, const uint32_t* vals, uint32_t* keys_out, uint32_t* vals_out, uint64_t stride, const uint32_t* d_len,
-                    const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t pass, uint32_t* d_hist, cudaStream_t st)
+                    const uint8_t* d_skip, uint32_t max_len, uint32_t nblk, uint32_t pass, uint32_t key_shift, uint32_t* d_hist, cudaStream_t st)
 {
     RsParams P{};
-    P.keys = keys; P.vals = vals; P.keys_out = keys_out; P.vals_out = vals_out; P.stride = stride; P.len = d_len; P.skip = d_skip; P.shift = pass * 8;
+    P.keys = keys; P.vals = vals; P.keys_out = keys_out; P.vals_out = vals_out; P.stride = stride; P.len = d_len; P.skip = d_skip; P.shift = key_shift + pass * 8;
     if (vals == nullptr)  // values are the element indices 0, 1, 2, ... (first pass of a sort): nothing to read
         return radix_launch<RS_IMPLICIT>(P, d_hist, pass, max_len, nblk, P_RS_SCATTER_IMPL, st);
     return radix_launch<RS_PAIRS>(P, d_hist, pass, max_len, nblk, P_RS_SCATTER, st);
