@@ -15,7 +15,7 @@ enum ProfId
     P_CRC, P_RS_HIST, P_RS_SCATTER_IMPL, P_RS_SCATTER, P_RS_SCATTER_U8, P_BWT_PERIOD, P_BWT_KEYS, P_BWT_HEADS, P_BWT_RANKS, P_BWT_PREPARE, P_BWT_GATHER, P_BWT_FINISH, P_BWT_MISC,
     P_MTF_SUMMARY, P_MTF_SCAN, P_MTF_APPLY, P_RLE_ENC_HEADS, P_RLE_ENC_LIT, P_RLE_ENC_SIZE, P_RLE_ENC_EMIT, P_RLE_DEC_EXIT, P_RLE_DEC_CHAIN,
     P_RLE_DEC_MARK, P_RLE_DEC_EXPAND, P_HUF_HIST, P_HUF_BUILD, P_HUF_BITS, P_HUF_PACK, P_HUF_DEC_TABLES, P_HUF_DEC_SYNC, P_HUF_DEC_SCAN,
-    P_HUF_DEC_WRITE, P_HUF_DEC_TRAILING, P_IBWT_WALK_LEN, P_IBWT_STITCH, P_IBWT_WALK_EMIT, P_GLUE, P_COUNT
+    P_HUF_DEC_WRITE, P_HUF_DEC_TRAILING, P_IBWT_WALK_LEN, P_IBWT_STITCH, P_IBWT_WALK_EMIT, P_IBWT_COPY, P_GLUE, P_COUNT
 };
 void prof_pre(int id, cudaStream_t st);
 void prof_post(int id, cudaStream_t st);
@@ -102,11 +102,13 @@ struct BwtInvArgs
     uint2*          d_walk;  // nblk * ibwt_kmax(max_n)
     uint32_t*       d_woff;  // same
     uint32_t*       d_orbit; // nblk
+    uint32_t*       d_ovf;   // optional: nblk * ibwt_ovf_words() -- overflow walker pool (needs d_tmp)
     uint8_t*        d_tmp;   // optional: nblk * ibwt_kmax(max_n) * ibwt_tmp_cap(max_n) bytes -- the first walk keeps the bytes it passes
 };
 uint32_t ibwt_tmp_cap(uint32_t max_n);
 uint32_t ibwt_row_stride(uint32_t max_n);
 uint32_t ibwt_kmax(uint32_t max_n);
+uint32_t ibwt_ovf_words();
 bool     bwt_inverse_batch(const BwtInvArgs& a, cudaStream_t st);
 
 // ---- mtf.cu -------------------------------------------------------------------------------

@@ -1113,16 +1113,21 @@ __device__ __forceinline__ uint32_t ib_rows(uint32_t n, uint32_t R) { return (n 
 // With `tmp`, the walk also keeps the first `cap` bytes it passes (F[idx] = W[idx] & 0xFF) in its own scratch
 // row: walks are about R steps long, so a row of 8R bytes holds nearly every walk completely, and the output
 // can then be assembled by a sequential copy instead of a second pass of dependent random loads.
+// A walk that fills its row (cap steps; about 3 walks in 10 000 at cap = 8R) takes a fresh walker slot from the block's
+// small overflow pool and goes on in that slot's row: it becomes two (or more) chained walkers, all complete in their
+// rows, and no second, emitting walk of a thousand dependent loads is needed for it. ovf[b*(IB_OVF+1)] counts the slots
+// taken, the words behind it keep the start rows of the overflow walkers.
+#define IB_OVF 64u
 __global__ void __launch_bounds__(IB_THREADS)
     ibwt_walk_len_kernel(const uint32_t* __restrict__ W, uint64_t stride, const uint32_t* __restrict__ len, const uint32_t* __restrict__ primary,
-                         uint32_t R, uint32_t kmax, uint2* __restrict__ walk /* (len, succ) */, uint32_t* __restrict__ woff,
+                         uint32_t R, uint32_t kmax, uint2* __restrict__ walk /* (len, succ) */, uint32_t* __restrict__ ovf,
                          uint8_t* __restrict__ tmp, uint32_t cap)
 {
     const uint32_t b = blockIdx.y;
     const uint32_t n = len[b];
     if (n == 0) return;
     const uint32_t K  = ib_rows(n, R);
-    const uint32_t w  = blockIdx.x * IB_THREADS + threadIdx.x;
+    uint32_t       w  = blockIdx.x * IB_THREADS + threadIdx.x;
     if (w > K) return;
     const uint32_t pi = primary[b];
     const uint32_t* Wb = W + (uint64_t) b * stride;
@@ -1155,6 +1160,21 @@ __global__ void __launch_bounds__(IB_THREADS)
             {
                 if (steps <= cap) row[(steps >> 4) - 1] = make_uint4(a0, a1, a2, a3);
                 a0 = a1 = a2 = a3 = 0;
+                if (steps == cap && ovf != nullptr && idx != pi && (idx & (R - 1u)) != 0)
+                {
+                    // row full and the walk goes on: continue as an overflow walker, if the pool has a slot left
+                    uint32_t* pool = ovf + (uint64_t) b * (IB_OVF + 1u);
+                    const uint32_t o = atomicAdd(pool, 1u);
+                    if (o < IB_OVF && K + 1u + o < kmax)
+                    {
+                        const uint32_t w2 = K + 1u + o;
+                        walk[(uint64_t) b * kmax + w] = make_uint2(steps, w2);
+                        pool[1u + o] = idx;
+                        w     = w2;
+                        row   = reinterpret_cast<uint4*>(tmp + ((uint64_t) b * kmax + w) * cap);
+                        steps = 0;
+                    }
+                }
             }
         } while (idx != pi && (idx & (R - 1u)) != 0);  // R is a power of two
         if ((steps & 15u) != 0 && steps <= cap) row[steps >> 4] = make_uint4(a0, a1, a2, a3);
@@ -1163,26 +1183,63 @@ __global__ void __launch_bounds__(IB_THREADS)
     walk[(uint64_t) b * kmax + w] = make_uint2(steps, succ);
 }
 
-// Assemble the output from the scratch rows: one warp per walk that is complete in its row.
+// number of walkers of block b: start rows, the primary row, the overflow slots taken
+__device__ __forceinline__ uint32_t ib_walkers(uint32_t K, const uint32_t* __restrict__ ovf, uint32_t b, uint32_t kmax)
+{
+    const uint32_t o = ovf ? min(ovf[(uint64_t) b * (IB_OVF + 1u)], IB_OVF) : 0u;
+    return min(K + 1u + o, kmax);
+}
+
+// Assemble the output from the scratch rows. A warp takes 32 consecutive walkers: every lane fetches the record of one
+// (offset, length: two coalesced loads instead of a chain of dependent ones per walker), then the warp copies the rows
+// one after the other, a row being a few aligned 32-bit words per lane.
+__device__ __forceinline__ void ibwt_copy_row(const uint8_t* __restrict__ row, uint8_t* __restrict__ dst, uint32_t m, uint32_t l)
+{
+    // aligned 32-bit stores: the row is 16-byte aligned, the destination is not -- every lane funnels the two row words
+    // that straddle its output word together; the few bytes before the first and after the last whole word go singly
+    const uint32_t mis = min(m, (uint32_t) ((4u - (reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u));
+    if (l < mis) dst[l] = row[l];
+    const uint32_t  nw    = (m - mis) >> 2;
+    const uint32_t* row32 = reinterpret_cast<const uint32_t*>(row);
+    uint32_t*       dst32 = reinterpret_cast<uint32_t*>(dst + mis);
+    for (uint32_t k = l; k < nw; k += 32)
+    {
+        const uint32_t sb = mis + 4u * k;
+        const uint32_t w0 = row32[sb >> 2];
+        const uint32_t w1 = (sb & 3u) ? row32[(sb >> 2) + 1u] : 0u;
+        dst32[k]          = __funnelshift_r(w0, w1, (sb & 3u) * 8u);
+    }
+    const uint32_t tail0 = mis + 4u * nw;
+    if (l < m - tail0) dst[tail0 + l] = row[tail0 + l];
+}
+
 __global__ void __launch_bounds__(256)
     ibwt_copy_kernel(const uint32_t* __restrict__ len, uint64_t stride, uint32_t R, uint32_t kmax, const uint2* __restrict__ walk,
                      const uint32_t* __restrict__ woff, const uint32_t* __restrict__ orbit, const uint8_t* __restrict__ tmp, uint32_t cap,
-                     uint8_t* __restrict__ out)
+                     uint8_t* __restrict__ out, const uint32_t* __restrict__ ovf)
 {
     const uint32_t b = blockIdx.y;
     const uint32_t n = len[b];
     if (n == 0 || orbit[b] < n) return;  // periodic blocks are replicated by the emit walk
-    const uint32_t K = ib_rows(n, R);
-    const uint32_t w = blockIdx.x * 8 + warp_id();
-    if (w > K) return;
-    const uint32_t o0 = woff[(uint64_t) b * kmax + w];
-    if (o0 == IB_INVALID) return;
-    const uint32_t steps = walk[(uint64_t) b * kmax + w].x;
-    if (steps > cap) return;  // did not fit: the emit walk does it
-    const uint8_t* row = tmp + ((uint64_t) b * kmax + w) * cap;
-    uint8_t*       ob  = out + (uint64_t) b * stride;
-    const uint32_t m   = min(steps, n - min(n, o0));
-    for (uint32_t t = lane_id(); t < m; t += 32) ob[o0 + t] = row[t];
+    const uint32_t K  = ib_rows(n, R);
+    const uint32_t NW = ib_walkers(K, ovf, b, kmax);
+    const uint32_t l  = lane_id();
+    const uint32_t w0 = (blockIdx.x * 8 + warp_id()) * 32;
+    if (w0 >= NW) return;
+    uint32_t my_off = IB_INVALID, my_steps = 0;
+    if (w0 + l < NW)
+    {
+        my_off   = woff[(uint64_t) b * kmax + w0 + l];
+        my_steps = walk[(uint64_t) b * kmax + w0 + l].x;
+        if (my_steps > cap) my_off = IB_INVALID;  // did not fit: the emit walk does it
+    }
+    uint8_t* ob = out + (uint64_t) b * stride;
+    for (uint32_t i = 0; i < 32; ++i)
+    {
+        const uint32_t o0 = __shfl_sync(BRA_FULL, my_off, i), steps = __shfl_sync(BRA_FULL, my_steps, i);
+        if (o0 == IB_INVALID) continue;
+        ibwt_copy_row(tmp + ((uint64_t) b * kmax + w0 + i) * cap, ob + o0, min(steps, n - min(n, o0)), l);
+    }
 }
 
 // Stitch: order the walks from the primary row. If the chain closes before n bytes are covered the
@@ -1194,7 +1251,7 @@ __global__ void __launch_bounds__(256)
 #define IB_TERM 0xFFFFFFFFu
 __global__ void __launch_bounds__(IB_STITCH_THREADS)
     ibwt_stitch_kernel(const uint32_t* __restrict__ len, const uint32_t* __restrict__ primary, uint32_t R, uint32_t kmax,
-                       const uint2* __restrict__ walk, uint32_t* __restrict__ woff, uint32_t* __restrict__ orbit)
+                       const uint2* __restrict__ walk, uint32_t* __restrict__ woff, uint32_t* __restrict__ orbit, const uint32_t* __restrict__ ovf)
 {
     extern __shared__ uint32_t s_dyn[];  // two (distance to the end of the cycle, link) pairs of kmax words each, ping-pong
     const uint32_t b = blockIdx.x;
@@ -1205,8 +1262,9 @@ __global__ void __launch_bounds__(IB_STITCH_THREADS)
         return;
     }
     const uint32_t K  = ib_rows(n, R);
+    const uint32_t NW = ib_walkers(K, ovf, b, kmax);  // walkers 0..NW-1 (K is the primary row's, the ones behind it are overflow walkers)
     uint32_t*      d0 = s_dyn, *n0 = s_dyn + kmax, *d1 = s_dyn + 2 * kmax, *n1 = s_dyn + 3 * kmax;
-    for (uint32_t w = threadIdx.x; w <= K; w += IB_STITCH_THREADS)
+    for (uint32_t w = threadIdx.x; w < NW; w += IB_STITCH_THREADS)
     {
         const uint2 e = walk[(uint64_t) b * kmax + w];
         d0[w]         = e.x;
@@ -1216,7 +1274,7 @@ __global__ void __launch_bounds__(IB_STITCH_THREADS)
     for (uint32_t span = 1;;)  // links every pointer has jumped so far
     {
         bool open = false;
-        for (uint32_t w = threadIdx.x; w <= K; w += IB_STITCH_THREADS)
+        for (uint32_t w = threadIdx.x; w < NW; w += IB_STITCH_THREADS)
         {
             const uint32_t nx = n0[w];
             uint32_t       dd = d0[w], nn = IB_TERM;
@@ -1233,12 +1291,12 @@ __global__ void __launch_bounds__(IB_STITCH_THREADS)
         t = n0; n0 = n1; n1 = t;
         const bool any = __syncthreads_or(open);
         span <<= 1;
-        // a walker on K's cycle is at most K+1 links from the cut; walkers on other cycles never reach it
-        if (!any || span > K + 1) break;
+        // a walker on K's cycle is at most NW links from the cut; walkers on other cycles never reach it
+        if (!any || span > NW) break;
     }
     const uint32_t q = d0[K];  // length of the cycle through the primary row
     const uint32_t pi = primary[b];
-    for (uint32_t w = threadIdx.x; w <= K; w += IB_STITCH_THREADS)
+    for (uint32_t w = threadIdx.x; w < NW; w += IB_STITCH_THREADS)
     {
         uint32_t off = IB_INVALID;
         if (n0[w] == IB_TERM && !(w != K && pi % R == 0 && w == pi / R)) off = q - d0[w];  // a start row equal to the primary row is walker K's double
@@ -1251,14 +1309,15 @@ __global__ void __launch_bounds__(IB_STITCH_THREADS)
 __global__ void __launch_bounds__(IB_THREADS)
     ibwt_walk_emit_kernel(const uint32_t* __restrict__ W, uint64_t stride, const uint32_t* __restrict__ len, const uint32_t* __restrict__ primary,
                           uint32_t R, uint32_t kmax, const uint2* __restrict__ walk, const uint32_t* __restrict__ woff,
-                          const uint32_t* __restrict__ orbit, uint8_t* __restrict__ out, uint32_t cap /* 0: no scratch rows */)
+                          const uint32_t* __restrict__ orbit, uint8_t* __restrict__ out, uint32_t cap /* 0: no scratch rows */,
+                          const uint32_t* __restrict__ ovf)
 {
     const uint32_t b = blockIdx.y;
     const uint32_t n = len[b];
     if (n == 0) return;
     const uint32_t K = ib_rows(n, R);
     const uint32_t w = blockIdx.x * IB_THREADS + threadIdx.x;
-    if (w > K) return;
+    if (w >= ib_walkers(K, ovf, b, kmax)) return;
     const uint32_t o0 = woff[(uint64_t) b * kmax + w];
     if (o0 == IB_INVALID) return;  // not on the primary row's orbit
     const uint32_t steps = walk[(uint64_t) b * kmax + w].x;
@@ -1266,7 +1325,7 @@ __global__ void __launch_bounds__(IB_THREADS)
     if (cap && q >= n && steps <= cap) return;  // assembled from the scratch rows by ibwt_copy_kernel
     const uint32_t* Wb   = W + (uint64_t) b * stride;
     uint8_t*        ob   = out + (uint64_t) b * stride;
-    uint32_t idx = (w == K) ? primary[b] : w * R;
+    uint32_t idx = (w == K) ? primary[b] : (w < K ? w * R : ovf[(uint64_t) b * (IB_OVF + 1u) + 1u + (w - K - 1u)]);
     if (q >= n)
     {
         // a walk's bytes are consecutive: gather four into one aligned 32-bit store (a byte store costs a whole L2 transaction)
@@ -1309,7 +1368,8 @@ uint32_t ibwt_row_stride(uint32_t max_n)
     return R;
 }
 uint32_t ibwt_tmp_cap(uint32_t max_n) { return 8u * ibwt_row_stride(max_n); }
-uint32_t ibwt_kmax(uint32_t max_n) { return (max_n + ibwt_row_stride(max_n) - 1) / ibwt_row_stride(max_n) + 1; }
+uint32_t ibwt_kmax(uint32_t max_n) { return (max_n + ibwt_row_stride(max_n) - 1) / ibwt_row_stride(max_n) + 1 + IB_OVF; }
+uint32_t ibwt_ovf_words() { return IB_OVF + 1u; }
 
 static bool bwt_inverse_chunk(const BwtInvArgs& a, cudaStream_t st)
 {
@@ -1317,13 +1377,15 @@ static bool bwt_inverse_chunk(const BwtInvArgs& a, cudaStream_t st)
     if (!radix_pass_u8_index_packed(a.d_in, a.d_W, a.stride, a.d_len, a.max_n, a.nblk, a.d_hist, st)) return false;
     const dim3 grid(bra_div_up(kmax, IB_THREADS), a.nblk);
     const uint32_t cap = a.d_tmp ? ibwt_tmp_cap(a.max_n) : 0u;
-    BRA_LAUNCH(P_IBWT_WALK_LEN, st, ibwt_walk_len_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_tmp, cap));
+    uint32_t* ovf = (a.d_tmp && a.d_ovf) ? a.d_ovf : nullptr;
+    if (ovf) BRA_CUDA_TRY(cudaMemsetAsync(ovf, 0, (size_t) a.nblk * (IB_OVF + 1u) * sizeof(uint32_t), st));
+    BRA_LAUNCH(P_IBWT_WALK_LEN, st, ibwt_walk_len_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, ovf, a.d_tmp, cap));
     const size_t stitch_smem = (size_t) kmax * 4 * sizeof(uint32_t);
-    BRA_CUDA_TRY(cudaFuncSetAttribute(ibwt_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 8200 * 4));
-    BRA_LAUNCH(P_IBWT_STITCH, st, ibwt_stitch_kernel<<<a.nblk, IB_STITCH_THREADS, stitch_smem, st>>>(a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit));
+    BRA_CUDA_TRY(cudaFuncSetAttribute(ibwt_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 8300 * 4));
+    BRA_LAUNCH(P_IBWT_STITCH, st, ibwt_stitch_kernel<<<a.nblk, IB_STITCH_THREADS, stitch_smem, st>>>(a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit, ovf));
     if (cap)
-        BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_copy_kernel<<<dim3(bra_div_up(kmax, 8), a.nblk), 256, 0, st>>>(a.d_len, a.stride, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_tmp, cap, a.d_out));
-    BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_walk_emit_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_out, cap));
+        BRA_LAUNCH(P_IBWT_COPY, st, ibwt_copy_kernel<<<dim3(bra_div_up(kmax, 256), a.nblk), 256, 0, st>>>(a.d_len, a.stride, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_tmp, cap, a.d_out, ovf));
+    BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_walk_emit_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_out, cap, ovf));
     BRA_CUDA_TRY(cudaGetLastError());
     return true;
 }

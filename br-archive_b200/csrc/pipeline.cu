@@ -74,7 +74,7 @@ struct DecWs
     uint8_t * R, *M, *L, *summ, *state, *sub_start, *t_exit, *t_entry, *wtmp, *phase;
     uint16_t* sub_count;
     uint32_t *W, *hist, *rlen, *clen, *nlen, *primary, *err, *seq_entry, *seq_exit, *seq_count, *end_bit, *changed, *t_tok, *t_ocnt, *woff,
-        *orbit;
+        *orbit, *ovf;
     uint2*         walk;
     bra_huf_dec_t* tabs;
 };
@@ -124,7 +124,7 @@ static void carve_dec(Arena& A, uint32_t S, uint32_t nb, DecWs& w)
     w.t_exit = A.take<uint8_t>(nb * rt * rle_dec_entries()); w.t_entry = A.take<uint8_t>(nb * rt);
     w.t_tok = A.take<uint32_t>(nb * rt * 32); w.t_ocnt = A.take<uint32_t>(nb * rt);
     const uint64_t km = ibwt_kmax(S);
-    w.walk = A.take<uint2>(nb * km); w.woff = A.take<uint32_t>(nb * km); w.orbit = A.take<uint32_t>(nb);
+    w.walk = A.take<uint2>(nb * km); w.woff = A.take<uint32_t>(nb * km); w.orbit = A.take<uint32_t>(nb); w.ovf = A.take<uint32_t>((uint64_t) nb * ibwt_ovf_words());
     w.wtmp = A.take<uint8_t>(nb * km * ibwt_tmp_cap(S));  // scratch rows of the inverse-BWT walks (about 8 bytes per input byte)
     w.rlen = A.take<uint32_t>(nb); w.clen = A.take<uint32_t>(nb); w.nlen = A.take<uint32_t>(nb); w.primary = A.take<uint32_t>(nb);
     w.err = A.take<uint32_t>(nb); w.end_bit = A.take<uint32_t>(nb); w.changed = A.take<uint32_t>(4);
@@ -409,7 +409,7 @@ bool decode_batch(bra_b200_ctx* c, const uint8_t* d_hdr, const uint8_t* d_payloa
 
     BwtInvArgs ia{};
     ia.d_in = w.L; ia.d_out = d_out; ia.stride = S; ia.d_len = w.nlen; ia.d_primary = w.primary; ia.max_n = S; ia.nblk = nb;
-    ia.d_W = w.W; ia.d_hist = w.hist; ia.d_walk = w.walk; ia.d_woff = w.woff; ia.d_orbit = w.orbit; ia.d_tmp = w.wtmp;
+    ia.d_W = w.W; ia.d_hist = w.hist; ia.d_walk = w.walk; ia.d_woff = w.woff; ia.d_orbit = w.orbit; ia.d_tmp = w.wtmp; ia.d_ovf = w.ovf;
     if (!bwt_inverse_batch(ia, st)) return false;
 
     if (!crc_blocks(d_out, S, w.nlen, 0, S, nb, nullptr, d_crc, st)) return false;

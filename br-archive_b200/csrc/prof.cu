@@ -16,7 +16,7 @@ static const char* const kProfNames[P_COUNT] = {
     "crc32c", "radix_hist", "radix_scatter_implicit", "radix_scatter", "radix_scatter_u8", "bwt_period", "bwt_keys", "bwt_heads", "bwt_ranks", "bwt_prepare", "bwt_gather",
     "bwt_finish", "bwt_misc", "mtf_summary", "mtf_scan", "mtf_apply", "rle_enc_heads", "rle_enc_lit", "rle_enc_size", "rle_enc_emit", "rle_dec_exit",
     "rle_dec_chain", "rle_dec_mark", "rle_dec_expand", "huf_hist", "huf_build", "huf_bits", "huf_pack", "huf_dec_tables", "huf_dec_sync",
-    "huf_dec_scan", "huf_dec_write", "huf_dec_trailing", "ibwt_walk_len", "ibwt_stitch", "ibwt_walk_emit", "glue"};
+    "huf_dec_scan", "huf_dec_write", "huf_dec_trailing", "ibwt_walk_len", "ibwt_stitch", "ibwt_walk_emit", "ibwt_copy", "glue"};
 
 struct ProfSlot
 {

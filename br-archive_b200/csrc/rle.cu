@@ -431,18 +431,50 @@ __global__ void __launch_bounds__(RD_THREADS)
     }
 }
 
-__global__ void rle_dec_chain_kernel(const uint32_t* __restrict__ rlen, uint32_t tiles, const uint8_t* __restrict__ t_exit,
-                                     uint8_t* __restrict__ t_entry, uint32_t nblk)
+// Entry offset of every tile: e(t+1) = exit_t[e(t)], a chain over up to a few thousand tiles per block. One warp per block
+// cuts it into 32 pieces: every lane first composes the exit maps of its piece for all RD_ENTRIES possible entries (the
+// chains of one lane are independent loads), lane 0 then links the 32 composed maps, and every lane replays its piece
+// from its now known entry -- three short dependent stretches instead of one long one.
+__global__ void __launch_bounds__(32) rle_dec_chain_kernel(const uint32_t* __restrict__ rlen, uint32_t tiles, const uint8_t* __restrict__ t_exit,
+                                                           uint8_t* __restrict__ t_entry, uint32_t nblk)
 {
-    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ uint8_t s_map[32][RD_ENTRIES + 2];
+    __shared__ uint8_t s_entry[32];
+    const uint32_t     b = blockIdx.x, l = threadIdx.x;
     if (b >= nblk) return;
     const uint32_t r      = rlen[b];
     const uint32_t ntiles = (r + RD_TILE - 1) / RD_TILE;
-    uint32_t       e      = 0;
-    for (uint32_t t = 0; t < ntiles; ++t)
+    const uint32_t per    = (ntiles + 31) / 32;
+    const uint32_t t0 = min(ntiles, l * per), t1 = min(ntiles, t0 + per);
+    const uint8_t* ex = t_exit + (uint64_t) b * tiles * RD_ENTRIES;
+    for (uint32_t e0 = 0; e0 < RD_ENTRIES; e0 += 10)
+    {
+        uint32_t e[10];
+#pragma unroll
+        for (int i = 0; i < 10; ++i) e[i] = min(e0 + i, (uint32_t) RD_ENTRIES - 1);
+        for (uint32_t t = t0; t < t1; ++t)
+#pragma unroll
+            for (int i = 0; i < 10; ++i) e[i] = ex[(uint64_t) t * RD_ENTRIES + e[i]];
+#pragma unroll
+        for (int i = 0; i < 10; ++i)
+            if (e0 + i < RD_ENTRIES) s_map[l][e0 + i] = (uint8_t) e[i];
+    }
+    __syncwarp();
+    if (l == 0)
+    {
+        uint32_t e = 0;
+        for (int c = 0; c < 32; ++c)
+        {
+            s_entry[c] = (uint8_t) e;
+            e          = s_map[c][e];
+        }
+    }
+    __syncwarp();
+    uint32_t e = s_entry[l];
+    for (uint32_t t = t0; t < t1; ++t)
     {
         t_entry[(uint64_t) b * tiles + t] = (uint8_t) e;
-        e = t_exit[((uint64_t) b * tiles + t) * RD_ENTRIES + e];
+        e = ex[(uint64_t) t * RD_ENTRIES + e];
     }
 }
 
@@ -602,7 +634,7 @@ bool rle_decode_batch(const RleDecArgs& a, cudaStream_t st)
     const uint32_t tiles = bra_div_up(a.max_r, RD_TILE);
     const dim3     grid(tiles, a.nblk);
     BRA_LAUNCH(P_RLE_DEC_EXIT, st, rle_dec_exit_kernel<<<grid, RD_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_exit));
-    BRA_LAUNCH(P_RLE_DEC_CHAIN, st, rle_dec_chain_kernel<<<bra_div_up(a.nblk, 32), 32, 0, st>>>(a.d_rlen, tiles, a.d_t_exit, a.d_t_entry, a.nblk));
+    BRA_LAUNCH(P_RLE_DEC_CHAIN, st, rle_dec_chain_kernel<<<a.nblk, 32, 0, st>>>(a.d_rlen, tiles, a.d_t_exit, a.d_t_entry, a.nblk));
     BRA_LAUNCH(P_RLE_DEC_MARK, st, rle_dec_mark_kernel<<<grid, RD_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_entry, a.d_t_tok, a.d_t_ocnt, a.d_err));
     if (a.size_only)
         BRA_LAUNCH(P_RLE_DEC_EXPAND, st, rle_dec_expand_kernel<<<grid, RD_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_tok, a.d_t_ocnt, a.d_err, nullptr, 0, 0xFFFFFFFFu,
