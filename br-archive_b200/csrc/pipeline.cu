@@ -94,7 +94,7 @@ static void carve_enc(Arena& A, uint32_t S, uint32_t nb, EncWs& w)
     w.tile_last = A.take<int>(nb * tiles);
     w.t_first_head = A.take<int>(nb * tiles); w.t_last_head = A.take<int>(nb * tiles);
     w.t_first_nl = A.take<int>(nb * tiles); w.t_last_nl = A.take<int>(nb * tiles);
-    w.t_cnt = A.take<uint32_t>(nb * tiles);
+    w.t_cnt = A.take<uint32_t>(nb * tiles + 64);  // (+ the RLE emit kernel's ticket word)
     w.t_bits = A.take<uint32_t>((uint64_t) nb * huf_enc_tiles((uint32_t) RS));
     const uint64_t segs = mtf_segments(S);
     w.summ = A.take<uint8_t>(nb * segs * 256); w.state = A.take<uint8_t>(nb * segs * 256); w.scnt = A.take<uint16_t>(nb * segs);

@@ -10,10 +10,10 @@
 //     literal; maximal stretches of consecutive literals are cut from their start into groups
 //     of 128, each prefixed by {group_len - 1}.
 // So every byte knows what it emits once it knows (run start, run end, stretch start, stretch
-// end): four max/min scans of head positions plus a sum scan for the output offset. Four
+// end): four max/min scans of head positions plus a sum scan for the output offset. Three
 // streaming kernels per block, each recomputing the cheap per-byte state from the input and
 // taking its cross-tile carries from the tile summaries the previous kernel wrote:
-//   heads -> literal flags -> sizes -> emit (+ the 256-bin histogram Huffman needs).
+//   heads -> literal flags -> sizes + emit (+ the 256-bin histogram Huffman needs; output offsets by look-back).
 //
 // DECODE. Token boundaries depend on all previous tokens. Per 1 KiB tile the map "entry offset
 // -> exit offset" is built for every possible entry (a token overhangs by at most 128 bytes)
@@ -225,20 +225,40 @@ __global__ void __launch_bounds__(RL_THREADS)
     }
 }
 
-// ---- passes 3 and 4: output size per tile, then emit ----------------------------------------------
-// EMIT == false: writes t_cnt. EMIT == true: needs t_cnt complete, writes bytes, r_len and histogram.
-template <bool EMIT>
-__global__ void __launch_bounds__(RL_THREADS)
-    rle_enc_out_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len, uint32_t tiles,
+// ---- pass 3: sizes, output offsets and emit in one kernel --------------------------------------------
+// The output offset of a tile is the sum of the sizes of the tiles before it: every tile publishes its size in a status
+// word and adds up its predecessors' by decoupled look-back (one warp, 32 predecessors per trip). Tiles are handed out
+// by ticket, a group of blocks interleaved, so a tile only ever waits for tiles that are running or done, and its
+// predecessors have usually published their inclusive sums already. Also writes r_len and the histogram Huffman needs.
+// status word: [31:30] 0 = empty, 1 = tile size, 2 = inclusive sum; [29:0] value
+#define RL_GROUP 16u
+#ifndef RL_EMIT_CTAS
+#define RL_EMIT_CTAS 4
+#endif
+__device__ __forceinline__ uint32_t rl_ld_status(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void rl_st_status(uint32_t* p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+__global__ void __launch_bounds__(RL_THREADS, RL_EMIT_CTAS)
+    rle_enc_out_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len, uint32_t tiles, uint32_t nblk,
                        const int* __restrict__ t_first_head, const int* __restrict__ t_last_head, const int* __restrict__ t_first_nl,
-                       const int* __restrict__ t_last_nl, uint32_t* __restrict__ t_cnt, uint8_t* __restrict__ out, uint64_t out_stride,
-                       uint32_t* __restrict__ r_len, uint32_t* __restrict__ hist)
+                       const int* __restrict__ t_last_nl, uint32_t* __restrict__ status /* [nblk][tiles], then the ticket counter; zeroed */,
+                       uint8_t* __restrict__ out, uint64_t out_stride, uint32_t* __restrict__ r_len, uint32_t* __restrict__ hist)
 {
     __shared__ int      red[34];
     __shared__ uint32_t ured[34];
-    __shared__ uint8_t  stage[EMIT ? RL_TILE + 64 : 4];
-    __shared__ uint32_t shist[EMIT ? 256 : 1];
-    const uint32_t b = blockIdx.y, t = blockIdx.x;
+    __shared__ uint8_t  stage[RL_TILE + 64];
+    __shared__ uint32_t shist[256];
+    __shared__ uint32_t s_ticket, s_out0;
+    if (threadIdx.x == 0) s_ticket = atomicAdd(status + (uint64_t) nblk * tiles, 1u);
+    __syncthreads();
+    const uint32_t per_group = RL_GROUP * tiles;
+    const uint32_t b = (s_ticket / per_group) * RL_GROUP + (s_ticket % per_group) % RL_GROUP, t = (s_ticket % per_group) / RL_GROUP;
+    if (b >= nblk) return;
     const uint32_t n = len[b];
     const uint32_t tile0 = t * RL_TILE;
     if (tile0 >= n) return;
@@ -292,20 +312,44 @@ __global__ void __launch_bounds__(RL_THREADS)
     }
     uint32_t tile_total;
     uint32_t off = block_excl_add(mysum, ured, &tile_total);
-    if (!EMIT)
     {
-        if (threadIdx.x == 0) t_cnt[(uint64_t) b * tiles + t] = tile_total;
-        return;
-    }
-    else
-    {
-        // output offset of the tile = sum of the counts of the tiles before it
-        uint32_t before = 0;
-        for (uint32_t i = threadIdx.x; i < t; i += RL_THREADS) before += t_cnt[(uint64_t) b * tiles + i];
-        uint32_t tile_out0;
-        block_excl_add(before, ured, &tile_out0);
-        shist[threadIdx.x]       = 0;
+        // output offset of the tile = sum of the sizes of the tiles before it (look-back by warp 0)
+        if (warp_id() == 0)
+        {
+            uint32_t* const st = status + (uint64_t) b * tiles;
+            const uint32_t  l  = lane_id();
+            if (l == 0) rl_st_status(st + t, ((t == 0 ? 2u : 1u) << 30) | tile_total);
+            uint32_t excl = 0;
+            if (t != 0)
+            {
+                int tt = (int) t - 1;
+                for (uint32_t trips = 0;; ++trips)
+                {
+                    if (trips > (1u << 24)) __trap();  // seconds of waiting: a predecessor never published -- fail loudly instead of hanging
+                    const uint32_t v     = tt - (int) l >= 0 ? rl_ld_status(st + (tt - (int) l)) : (2u << 30);  // before tile 0: inclusive sum 0
+                    const uint32_t incl  = __ballot_sync(BRA_FULL, (v >> 30) == 2u);
+                    const uint32_t empty = __ballot_sync(BRA_FULL, (v >> 30) == 0u);
+                    const uint32_t upto  = incl ? (uint32_t) (__ffs(incl) - 1) : 31u;  // lanes 0..upto are summed
+                    const uint32_t need  = upto == 31u ? 0xFFFFFFFFu : ((2u << upto) - 1u);
+                    if (empty & need)
+                    {
+                        __nanosleep(100);
+                        continue;  // a tile in the window has not published yet
+                    }
+                    uint32_t x = l <= upto ? (v & 0x3FFFFFFFu) : 0u;
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(BRA_FULL, x, d);
+                    excl += x;
+                    if (incl) break;
+                    tt -= 32;
+                }
+                if (l == 0) rl_st_status(st + t, (2u << 30) | (excl + tile_total));
+            }
+            if (l == 0) s_out0 = excl;
+        }
+        shist[threadIdx.x] = 0;
         __syncthreads();
+        const uint32_t tile_out0 = s_out0;
 #pragma unroll
         for (int i = 0; i < 16; ++i)
         {
@@ -357,11 +401,10 @@ bool rle_encode_batch(const RleEncArgs& a, cudaStream_t st)
     BRA_LAUNCH(P_RLE_ENC_HEADS, st, rle_enc_heads_kernel<<<grid, RL_THREADS, 0, st>>>(a.d_in, a.stride, a.d_len, tiles, a.d_t_first_head, a.d_t_last_head));
     BRA_LAUNCH(P_RLE_ENC_LIT, st, rle_enc_lit_kernel<<<grid, RL_THREADS, 0, st>>>(a.d_in, a.stride, a.d_len, tiles, a.d_t_first_head, a.d_t_last_head, a.d_t_first_nl,
                                                     a.d_t_last_nl));
-    BRA_LAUNCH(P_RLE_ENC_SIZE, st, rle_enc_out_kernel<false><<<grid, RL_THREADS, 0, st>>>(a.d_in, a.stride, a.d_len, tiles, a.d_t_first_head, a.d_t_last_head,
-                                                           a.d_t_first_nl, a.d_t_last_nl, a.d_t_cnt, nullptr, 0, nullptr, nullptr));
-    BRA_LAUNCH(P_RLE_ENC_EMIT, st, rle_enc_out_kernel<true><<<grid, RL_THREADS, 0, st>>>(a.d_in, a.stride, a.d_len, tiles, a.d_t_first_head, a.d_t_last_head,
-                                                          a.d_t_first_nl, a.d_t_last_nl, a.d_t_cnt, a.d_out, a.out_stride, a.d_rlen,
-                                                          a.d_hist));
+    BRA_CUDA_TRY(cudaMemsetAsync(a.d_t_cnt, 0, ((size_t) a.nblk * tiles + 1) * sizeof(uint32_t), st));
+    const uint32_t ctas = bra_div_up(a.nblk, RL_GROUP) * RL_GROUP * tiles;
+    BRA_LAUNCH(P_RLE_ENC_EMIT, st, rle_enc_out_kernel<<<ctas, RL_THREADS, 0, st>>>(a.d_in, a.stride, a.d_len, tiles, a.nblk, a.d_t_first_head, a.d_t_last_head,
+                                                    a.d_t_first_nl, a.d_t_last_nl, a.d_t_cnt, a.d_out, a.out_stride, a.d_rlen, a.d_hist));
     BRA_CUDA_TRY(cudaGetLastError());
     return true;
 }
@@ -646,7 +689,7 @@ bool rle_decode_batch(const RleDecArgs& a, cudaStream_t st)
     return true;
 }
 
-uint32_t rle_enc_tiles(uint32_t max_n) { return bra_div_up(max_n, RL_TILE); }
+uint32_t rle_enc_tiles(uint32_t max_n) { return bra_div_up(max_n, RL_TILE) + 1; }  // (+1: the ticket word behind the per-tile status)
 uint32_t rle_dec_tiles(uint32_t max_r) { return bra_div_up(max_r, RD_TILE); }
 uint32_t rle_dec_entries() { return RD_ENTRIES; }
 
