@@ -757,14 +757,23 @@ __global__ void __launch_bounds__(EW_THREADS, 4)
     }
 }
 
+// Heads of a freshly sorted order plus the group statistics the finisher decision looks at, warp-striped.
+//   KIND 0: initial sort -- head <=> the sorted key differs from its left neighbour
+//   KIND 1: packed round -- head <=> (key, second key) differs; also unpacks the rotation indices into sa_out
+// Statistics: every group piece between two consecutive heads counts with its length; pieces are cut at tile borders
+// only (a group spanning a border counts as two pieces -- the decision it feeds is a cost heuristic, not a correctness
+// condition, and a tile without any head still reports a piece of 4096).
+template <int KIND>
 __global__ void __launch_bounds__(EW_THREADS)
-    bwt_heads_packed_kernel(const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo, uint64_t stride, const uint32_t* __restrict__ period,
-                            const uint8_t* __restrict__ skip, uint8_t* __restrict__ flags, uint32_t* __restrict__ sa_out, int* __restrict__ tile_last,
-                            uint32_t tiles, uint32_t* __restrict__ ngroups, uint32_t* __restrict__ tile_heads)
+    bwt_heads_stats_kernel(const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo, uint64_t stride, const uint32_t* __restrict__ period,
+                           const uint8_t* __restrict__ skip, uint8_t* __restrict__ flags, uint32_t* __restrict__ sa_out, int* __restrict__ tile_last,
+                           uint32_t tiles, uint32_t* __restrict__ ngroups, uint32_t* __restrict__ tile_heads, uint32_t* __restrict__ maxgroup,
+                           unsigned long long* __restrict__ sumsq)
 {
-    __shared__ int      s_last[8];
-    __shared__ uint32_t s_cnt[8];
-    const uint32_t      b = blockIdx.y;
+    __shared__ int                s_first[8], s_last[8];
+    __shared__ uint32_t           s_cnt[8], s_mg[8];
+    __shared__ unsigned long long s_sq[8];
+    const uint32_t                b = blockIdx.y;
     if (skip[b]) return;
     const uint32_t p     = period[b];
     const uint32_t tile0 = blockIdx.x * EW_TILE;
@@ -772,64 +781,108 @@ __global__ void __launch_bounds__(EW_THREADS)
     const uint64_t base = (uint64_t) b * stride;
     const uint32_t w = warp_id(), l = lane_id();
     const uint32_t seg0 = tile0 + w * 512;
-    int            last = -1;
-    uint32_t       cnt  = 0;
-    uint32_t       xh[16], xl[16];
+    int                first = -1, last = -1;
+    uint32_t           cnt = 0, mg = 0;
+    unsigned long long sq = 0;
+    uint32_t           xh[16], xl[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r)
     {
         const uint32_t j = seg0 + r * 32 + l;
         xh[r]            = j < p ? hi[base + j] : 0u;
-        xl[r]            = j < p ? lo[base + j] : 0u;
+        xl[r]            = (KIND == 1 && j < p) ? lo[base + j] : 0u;
     }
     // the element left of the warp's first slot
     uint32_t ph = 0, pl = 0;
     if (seg0 > 0 && seg0 < p)
     {
         ph = hi[base + seg0 - 1];
-        pl = lo[base + seg0 - 1] >> 22;
+        if (KIND == 1) pl = lo[base + seg0 - 1] >> 22;
     }
 #pragma unroll
     for (int r = 0; r < 16; ++r)
     {
-        const uint32_t j  = seg0 + r * 32 + l;
-        const uint32_t s2 = xl[r] >> 22;
+        const uint32_t j0r = seg0 + r * 32;
+        const uint32_t j   = j0r + l;
+        const uint32_t s2  = xl[r] >> 22;
         uint32_t       lh = __shfl_up_sync(BRA_FULL, xh[r], 1), ll = __shfl_up_sync(BRA_FULL, s2, 1);
         if (l == 0)
         {
             lh = ph;
             ll = pl;
         }
-        const bool     head = j < p && (j == 0 || xh[r] != lh || s2 != ll);
+        const bool     head = j < p && (j == 0 || xh[r] != lh || (KIND == 1 && s2 != ll));
         const uint32_t hb   = __ballot_sync(BRA_FULL, head);
-        if (hb) last = (int) (seg0 + r * 32 + (31 - __clz(hb)));
+        if (head)
+        {
+            // the piece this head closes starts at the previous head of the warp's slots (pieces that start before them
+            // are closed below, once the warps know of each other)
+            const uint32_t below = hb & lanemask_lt();
+            const int      prev  = below ? (int) (j0r + (31 - __clz(below))) : last;
+            if (prev >= 0)
+            {
+                const uint32_t g = j - (uint32_t) prev;
+                mg               = max(mg, g);
+                if (g > 1) sq += (unsigned long long) g * g;
+            }
+        }
+        if (hb)
+        {
+            if (first < 0) first = (int) (j0r + (__ffs(hb) - 1));
+            last = (int) (j0r + (31 - __clz(hb)));
+        }
         cnt += __popc(hb);
         if (j < p)
         {
-            flags[base + j]  = head ? 1 : 0;
-            sa_out[base + j] = xl[r] & 0x3FFFFFu;
+            flags[base + j] = head ? 1 : 0;
+            if (KIND == 1) sa_out[base + j] = xl[r] & 0x3FFFFFu;
         }
         ph = __shfl_sync(BRA_FULL, xh[r], 31);
         pl = __shfl_sync(BRA_FULL, s2, 31);
     }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        mg = max(mg, __shfl_xor_sync(BRA_FULL, mg, d));
+        sq += __shfl_xor_sync(BRA_FULL, sq, d);
+    }
     if (l == 0)
     {
-        s_last[w] = last;
-        s_cnt[w]  = cnt;
+        s_first[w] = first;
+        s_last[w]  = last;
+        s_cnt[w]   = cnt;
+        s_mg[w]    = mg;
+        s_sq[w]    = sq;
     }
     __syncthreads();
     if (threadIdx.x == 0)
     {
-        int      L = -1;
-        uint32_t c = 0;
+        int                L = -1;
+        uint32_t           c = 0, m = 0;
+        unsigned long long q = 0;
+        int                open = (int) tile0;  // start of the piece still open: the tile border, then the last head seen
         for (int i = 0; i < 8; ++i)
         {
-            L = max(L, s_last[i]);
             c += s_cnt[i];
+            m = max(m, s_mg[i]);
+            q += s_sq[i];
+            if (s_first[i] >= 0)
+            {
+                const uint32_t g = (uint32_t) (s_first[i] - open);  // 0 when the piece starts right at a head
+                m                = max(m, g);
+                if (g > 1) q += (unsigned long long) g * g;
+                open = s_last[i];
+                L    = s_last[i];
+            }
         }
+        const uint32_t g = min(p, tile0 + EW_TILE) - (uint32_t) open;  // the piece that runs into the next tile, or ends the block
+        m                = max(m, g);
+        if (g > 1) q += (unsigned long long) g * g;
         tile_last[(uint64_t) b * tiles + blockIdx.x] = L;
         if (tile_heads) tile_heads[(uint64_t) b * tiles + blockIdx.x] = c;
         atomicAdd(&ngroups[b], c);
+        atomicMax(&maxgroup[b], m);
+        if (q) atomicAdd(&sumsq[b], q);
     }
 }
 
@@ -981,10 +1034,8 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     const dim3 g1(bra_div_up(nblk, 128));
     BRA_CUDA_TRY(cudaMemsetAsync(a.d_fin, 0, nblk, st));
     BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_done, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
-    BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<0><<<grid, EW_THREADS, 0, st>>>(kA, vA, nullptr, 0, a.stride, a.d_period, a.d_done, nullptr, fcur, a.d_tile_last, tiles,
-                                                      a.d_ngroups, a.d_tile_heads));
-    BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fcur, nullptr, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
-                                                                             a.d_maxgroup, a.d_sumsq, a.d_ngroups, 0, nullptr));
+    BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_stats_kernel<0><<<grid, EW_THREADS, 0, st>>>(kA, nullptr, a.stride, a.d_period, a.d_done, fcur, nullptr, a.d_tile_last, tiles, a.d_ngroups,
+                                                                                   a.d_tile_heads, a.d_maxgroup, a.d_sumsq));
     // the ranks themselves are written when (and for the blocks that) a doubling round follows
     const uint8_t* ranks_old     = nullptr;
 
@@ -1049,6 +1100,8 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
         const uint32_t round_bits = dense ? dense_bits : key_bits, round_passes = (round_bits + 7) / 8;
         // the kernel that assigns the ranks also counts their digits for every pass of the round's sort
         BRA_CUDA_TRY(cudaMemsetAsync(a.d_hist, 0, ghist_bytes, st));
+        // (a warp-striped version of the two rank kernels -- coalesced loads, ballot scans -- was measured slower: 17.7 against
+        // 15.5 ms per GiB of text; the scatter, not the bookkeeping, is what they wait for)
         if (dense)
             BRA_LAUNCH(P_BWT_RANKS, st, bwt_dense_ranks_kernel<<<grid, EW_THREADS, 0, st>>>(vA, fcur, a.stride, a.d_period, a.d_done, a.d_tile_heads, tiles, rk, a.d_ngroups,
                                                                                         round_passes, a.d_hist));
@@ -1069,8 +1122,8 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
                 std::swap(kA, kB);
                 std::swap(vA, vB);
             }
-            BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_packed_kernel<<<grid, EW_THREADS, 0, st>>>(kA, vA, a.stride, a.d_period, a.d_done, fnext, vB, a.d_tile_last, tiles, a.d_ngroups,
-                                                                                         a.d_tile_heads));
+            BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_stats_kernel<1><<<grid, EW_THREADS, 0, st>>>(kA, vA, a.stride, a.d_period, a.d_done, fnext, vB, a.d_tile_last, tiles, a.d_ngroups,
+                                                                                           a.d_tile_heads, a.d_maxgroup, a.d_sumsq));
             std::swap(vA, vB);  // the plain rotation indices
         }
         else
@@ -1087,8 +1140,9 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(nullptr, vA, rk, h, a.stride, a.d_period, a.d_done, fcur, fnext, a.d_tile_last, tiles,
                                                               a.d_ngroups, a.d_tile_heads));
         }
-        BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
-                                                                                 a.d_maxgroup, a.d_sumsq, a.d_ngroups, 0, nullptr));
+        if (max_n > BWT_PACK_MAX_N)  // (the packed path's head kernel has produced the group statistics already)
+            BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
+                                                                                     a.d_maxgroup, a.d_sumsq, a.d_ngroups, 0, nullptr));
         std::swap(fcur, fnext);
         ranks_old     = dense ? nullptr : fnext;  // the flags of before this round; after a round on group numbers every rank is rewritten
         h *= 2;
