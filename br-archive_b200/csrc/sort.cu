@@ -246,6 +246,9 @@ __device__ __forceinline__ void rs_tile(const RsParams& P, RsSmem& S, const uint
         }
         uint32_t* const tile_status = P.status + ((uint64_t) b * P.tiles) * RS_RADIX + d;  // + tile * RS_RADIX
         st_relaxed_u32(tile_status + (uint64_t) t * RS_RADIX, ((t == 0 ? RS_FLAG_INCL : RS_FLAG_LOCAL) << 30) | cnt);
+        // the nearest predecessor's word is fetched now and looked at after the scan below: with the blocks interleaved it
+        // nearly always carries the inclusive prefix already, and its L2 latency hides behind the scan
+        const uint32_t early = t != 0 ? ld_relaxed_u32(tile_status + (uint64_t) (t - 1) * RS_RADIX) : 0u;
         const uint32_t dstart = block_excl_add(cnt, S.red, nullptr);  // start of the digit's run in the sorted tile
         uint32_t       run    = dstart;
 #pragma unroll
@@ -262,6 +265,12 @@ __device__ __forceinline__ void rs_tile(const RsParams& P, RsSmem& S, const uint
             int      tt    = (int) t - 1;
             bool     open  = true;
             uint32_t trips = 0;
+            if ((early >> 30) != 0u)
+            {
+                excl = early & RS_VAL_MASK;
+                --tt;
+                open = (early >> 30) != RS_FLAG_INCL;
+            }
             while (open)
             {
                 if (++trips > (1u << 24)) __trap();  // seconds of waiting: a predecessor never published -- fail loudly instead of hanging
@@ -412,8 +421,10 @@ static bool radix_launch(RsParams& P, uint32_t* d_hist, uint32_t pass, uint32_t 
     P.nblk   = nblk;
     static const uint32_t thresh = getenv("BRA_B200_MATCH_MAX") ? (uint32_t) atoi(getenv("BRA_B200_MATCH_MAX")) : 16u;  // tuning switch, read once
     P.match_max_distinct = thresh;
-    // blocks whose tiles are interleaved in ticket order: as many as keep their working sets (16 bytes per element) in L2
-    P.group  = (uint32_t) std::max<uint64_t>(1, std::min<uint64_t>(16, (64ull << 20) / (16ull * P.tiles * RS_TILE)));
+    // blocks whose tiles are interleaved in ticket order (each block streams through its own 256 write fronts: the partially
+    // written lines of sixteen blocks are a negligible share of L2)
+    static const uint32_t group_max = getenv("BRA_B200_RS_GROUP") ? (uint32_t) std::max(1, atoi(getenv("BRA_B200_RS_GROUP"))) : 64u;  // tuning switch, read once
+    P.group  = std::min<uint32_t>(group_max, nblk);
     P.ghist  = d_hist + (size_t) pass * RS_RADIX;
     P.ticket = d_hist + (size_t) nblk * RS_GHIST_STRIDE;
     P.status = P.ticket + 64;
