@@ -458,3 +458,25 @@ static inline uint32_t bra_stage_plan(uint64_t nblk, uint32_t hb, uint32_t* plan
     if (tail2) plan[n++] = (uint32_t) tail2;
     return n;
 }
+
+// Encoding moves a block in and a fifth of it out (or, at worst, all of it): only the first input copy is exposed, the
+// output copies are short. So a short head (an eighth of the job: its kernels run as long as the next input copy takes)
+// and then stages as wide as the context allows -- every further stage would only add its few milliseconds of
+// latency-bound kernels. Writes at most nblk / hb + 2 entries; returns the count.
+static inline uint32_t bra_stage_plan_encode(uint64_t nblk, uint32_t hb, uint32_t head_div, uint32_t* plan)
+{
+    uint32_t n = 0;
+    if (nblk == 0 || hb == 0) return 0;
+    if (head_div < 2) head_div = 2;
+    uint64_t head = nblk / head_div;
+    if (head < 16) head = nblk < 32 ? nblk / 2 : 16;
+    if (head > hb) head = hb;
+    if (head) plan[n++] = (uint32_t) head;
+    for (uint64_t left = nblk - head; left > 0;)
+    {
+        const uint64_t take = left < hb ? left : hb;
+        plan[n++] = (uint32_t) take;
+        left -= take;
+    }
+    return n;
+}

@@ -78,5 +78,6 @@ int hl_rot_cmp(const uint8_t* T, uint32_t p, uint32_t a, uint32_t c, uint32_t fr
 
 // host-path pipeline plan (bra_stage_plan); `plan` must hold nblk / hb + 4 entries
 uint32_t hl_stage_plan(uint64_t nblk, uint32_t hb, uint32_t* plan) { return bra_stage_plan(nblk, hb, plan); }
+uint32_t hl_stage_plan_encode(uint64_t nblk, uint32_t hb, uint32_t head_div, uint32_t* plan) { return bra_stage_plan_encode(nblk, hb, head_div, plan); }
 
 }  // extern "C"

@@ -206,6 +206,13 @@ inline std::vector<uint32_t> stage_plan(uint64_t nblk, uint32_t hb)
     plan.resize(bra_stage_plan(nblk, hb, plan.data()));
     return plan;
 }
+inline std::vector<uint32_t> stage_plan_encode(uint64_t nblk, uint32_t hb)
+{
+    static const uint32_t head_div = getenv("BRA_B200_ENC_HEAD_DIV") ? (uint32_t) atoi(getenv("BRA_B200_ENC_HEAD_DIV")) : 8u;  // tuning switch, read once
+    std::vector<uint32_t> plan(nblk / std::max(1u, hb) + 4);
+    plan.resize(bra_stage_plan_encode(nblk, hb, head_div, plan.data()));
+    return plan;
+}
 }  // namespace
 
 // Three streams: input copies run one stage ahead of the kernels, output copies one stage behind
@@ -229,7 +236,7 @@ int encode_host_impl(bra_b200_ctx_t* c, const uint8_t* in, uint64_t total, uint8
     const uint32_t HB = stage_blocks(bra_b200_max_batch(c));
     const uint64_t PS = bra_b200_payload_stride(c);
     const uint64_t nblk_total = (total + S - 1) / S;
-    const std::vector<uint32_t> plan = stage_plan(nblk_total, HB);
+    const std::vector<uint32_t> plan = stage_plan_encode(nblk_total, HB);
     const uint64_t        nstage = plan.size();
     std::vector<uint64_t> first(nstage + 1, 0);  // first block of every stage
     for (uint64_t i = 0; i < nstage; ++i) first[i + 1] = first[i] + plan[i];

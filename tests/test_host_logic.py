@@ -123,6 +123,20 @@ def test_stage_plan_covers_every_block(hl):
     plan = np.zeros(8, dtype=np.uint32)
     k = hl.hl_stage_plan(1024, 1024, plan.ctypes.data_as(u32p))
     assert plan[:k].tolist() == [102, 602, 256, 64]  # short head, wide middle, shrinking tail
+    # encoding: short head, then stages as wide as the context allows (output copies are short, nothing to taper)
+    hl.hl_stage_plan_encode.restype = C.c_uint32
+    hl.hl_stage_plan_encode.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, u32p]
+    for hb in (1, 2, 3, 4, 8, 16, 64, 256, 1024, 32768):
+        for n in list(range(1, 700)) + [1023, 1024, 1025, 4096, 5000, 65536, 100003]:
+            for div in (0, 2, 8, 16):
+                plan = np.zeros(n // hb + 4, dtype=np.uint32)
+                k = hl.hl_stage_plan_encode(n, hb, div, plan.ctypes.data_as(u32p))
+                assert 1 <= k <= len(plan)
+                p = plan[:k]
+                assert p.min() >= 1 and p.max() <= hb and int(p.sum()) == n, (n, hb, div, p.tolist())
+    plan = np.zeros(8, dtype=np.uint32)
+    k = hl.hl_stage_plan_encode(1024, 1024, 8, plan.ctypes.data_as(u32p))
+    assert plan[:k].tolist() == [128, 896]
 
 
 def test_finisher_rotation_compare_is_exact_to_the_byte(hl):

@@ -7,11 +7,11 @@ import json
 import sys
 from collections import defaultdict
 
-FAMILY = [("rs_onesweep_kernel<(int)0>", "radix_scatter"), ("rs_onesweep_kernel<(int)1>", "radix_scatter_implicit"), ("rs_onesweep_kernel<(int)2>", "radix_scatter_u8"),
-          ("bwt_ranks_kernel", "bwt_ranks"), ("bwt_dense_ranks_kernel", "bwt_ranks"), ("bwt_heads_kernel", "bwt_heads"), ("bwt_dbl_prepare_kernel", "bwt_prepare"),
+FAMILY = [("rs_onesweep_kernel<0>", "radix_scatter"), ("rs_onesweep_kernel<1>", "radix_scatter_implicit"), ("rs_onesweep_kernel<2>", "radix_scatter_u8"),
+          ("bwt_ranks_kernel<2>", "bwt_ranks"), ("bwt_dense_ranks_kernel", "bwt_ranks"), ("bwt_heads_stats_kernel<1>", "bwt_heads"), ("bwt_heads_kernel<1>", "bwt_heads"), ("bwt_dbl_prepare", "bwt_prepare"),
           ("bwt_finish_kernel", "bwt_finish"), ("bwt_gather_kernel", "bwt_gather"), ("mtf_lane_kernel", "mtf_apply"), ("mtf_enc_summary_kernel", "mtf_summary"),
           ("ibwt_walk_len_kernel", "ibwt_walk_len"), ("ibwt_walk_emit_kernel", "ibwt_walk_emit"), ("crc_raw_kernel", "crc32c"), ("huf_dec_sync_kernel", "huf_dec_sync"),
-          ("huf_dec_write_kernel", "huf_dec_write"), ("huf_pack_kernel", "huf_pack"), ("rle_enc_out_kernel<(bool)1>", "rle_enc_emit"),
+          ("huf_dec_write_kernel", "huf_dec_write"), ("huf_pack_kernel", "huf_pack"), ("rle_enc_out_kernel", "rle_enc_emit"),
           ("rle_dec_expand_kernel", "rle_dec_expand"), ("rle_dec_mark_kernel", "rle_dec_mark")]
 
 
@@ -55,17 +55,22 @@ def main():
               f"{(a['rd'] + a['wr']) / 1e9 / (ms / 1e3) if ms else 0:9.0f} {a['occ'] / ms if ms else 0:5.1f} {a['bank']:11.3g} {int(a['regs']):4d} {a['winst'] / 1e9:7.3f}")
     print(f"total kernel time {total:.3f} ms over {sum(int(a['n']) for a in agg.values())} launches (cold-cache, serialised; shares are what compares with the live brackets)")
     if len(sys.argv) > 3 and sys.argv[2] == "--traffic":
+        # DRAM bytes per element of the FULL-BATCH launches only (the end-to-end stages of the same run launch the same
+        # kernels on fewer blocks): per family, the launches lasting at least 80 % of the family's longest one
         elems = float(sys.argv[3])
-        fam = defaultdict(lambda: [0.0, 0])
+        fam = defaultdict(list)
         for (_, name), m in launches.items():
             s = short(name)
             for pat, f in FAMILY:
                 if s.startswith(pat):
-                    fam[f][0] += m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)
-                    fam[f][1] += 1
+                    fam[f].append((m.get("gpu__time_duration.sum", 0), m.get("dram__bytes_read.sum", 0) + m.get("dram__bytes_write.sum", 0)))
                     break
-        print(json.dumps({f: round(b / n / elems, 2) for f, (b, n) in sorted(fam.items())}, indent=1))
-
+        out = {}
+        for f, rows in sorted(fam.items()):
+            gmax = max(g for g, _ in rows)
+            full = [b for g, b in rows if g >= 0.8 * gmax]
+            out[f] = round(sum(full) / len(full) / elems, 2)
+        print(json.dumps(out, indent=1))
 
 if __name__ == "__main__":
     main()
