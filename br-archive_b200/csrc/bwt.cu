@@ -39,61 +39,102 @@ namespace bra {
 // ------------------------------------------------------------------------------------------------
 // 1. period detection
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) bwt_period_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len,
-                                                         const uint32_t* __restrict__ div_vals, const uint32_t* __restrict__ div_off,
-                                                         const uint32_t* __restrict__ div_cnt, uint8_t* __restrict__ bad, uint32_t bad_stride)
+// Divisors are tried in ascending order, so the first one that survives is the smallest period. A cheap pretest on
+// the first 32 bytes refutes almost every divisor of almost every block (all of them on text and random data: the full
+// comparison is then never launched); a block with a surviving candidate compares itself with its shift by that
+// candidate, tile by tile, and moves on to the next unrefuted divisor if it fails. While a block is unresolved period[b]
+// holds 0x80000000 | index of its current candidate.
+#define BWT_PERIOD_PENDING 0x80000000u
+__global__ void __launch_bounds__(32) bwt_period_pretest_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len,
+                                                                const uint32_t* __restrict__ div_vals, const uint32_t* __restrict__ div_off,
+                                                                const uint32_t* __restrict__ div_cnt, uint8_t* __restrict__ bad, uint32_t bad_stride,
+                                                                uint32_t* __restrict__ period, uint32_t* __restrict__ pending)
 {
-    const uint32_t b = blockIdx.y;
+    const uint32_t b = blockIdx.x;
     const uint32_t n = len[b];
-    const uint32_t tile0 = blockIdx.x * EW_TILE;
-    if (tile0 >= n) return;
-    const uint8_t* T    = in + (uint64_t) b * stride;
-    const uint32_t tend = min(n, tile0 + EW_TILE);
-    const uint32_t cnt  = div_cnt[b];
-    const uint32_t* dv  = div_vals + div_off[b];
-    const uint32_t q    = min(n, 32u);
+    const uint8_t* T   = in + (uint64_t) b * stride;
+    const uint32_t cnt = div_cnt[b];
+    const uint32_t* dv = div_vals + div_off[b];
+    const uint32_t q   = min(n, 32u);
+    const uint32_t l   = lane_id();
+    const uint8_t  mine = l < q ? T[l] : 0;
+    uint32_t       first = cnt;
     for (uint32_t di = 0; di < cnt; ++di)
     {
-        const uint32_t d = dv[di];  // proper divisor of n
-        // cheap uniform pre-test on the first 32 bytes
-        const uint32_t l  = lane_id();
+        const uint32_t d  = dv[di];  // proper divisor of n
         bool           ne = false;
         if (l < q)
         {
             uint32_t j = l + d;
             if (j >= n) j -= n;
-            ne = T[l] != T[j];
+            ne = mine != T[j];
         }
-        if (__any_sync(BRA_FULL, ne))  // same outcome in every warp of the CTA: d is not a period
+        if (__any_sync(BRA_FULL, ne))
         {
-            if (threadIdx.x == 0) bad[(uint64_t) b * bad_stride + di] = 1;
-            continue;
+            if (l == 0) bad[(uint64_t) b * bad_stride + di] = 1;
         }
-        bool mism = false;
-        for (uint32_t i = tile0 + threadIdx.x; i < tend; i += 256)
+        else if (first == cnt)
+            first = di;
+    }
+    if (l == 0)
+    {
+        if (first == cnt)
+            period[b] = n;  // no divisor left: the block is primitive
+        else
         {
-            uint32_t j = i + d;
-            if (j >= n) j -= n;
-            mism |= T[i] != T[j];
+            period[b] = BWT_PERIOD_PENDING | first;
+            atomicAdd(pending, 1u);
         }
-        if (__syncthreads_or(mism) && threadIdx.x == 0) bad[(uint64_t) b * bad_stride + di] = 1;
     }
 }
 
-__global__ void bwt_period_select_kernel(const uint32_t* __restrict__ len, const uint32_t* __restrict__ div_vals,
-                                         const uint32_t* __restrict__ div_off, const uint32_t* __restrict__ div_cnt,
-                                         const uint8_t* __restrict__ bad, uint32_t bad_stride, uint32_t* __restrict__ period, uint32_t nblk)
+__global__ void __launch_bounds__(256) bwt_period_full_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ len,
+                                                              const uint32_t* __restrict__ div_vals, const uint32_t* __restrict__ div_off,
+                                                              const uint32_t* __restrict__ period, uint8_t* __restrict__ bad, uint32_t bad_stride)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t v = period[b];
+    if (!(v & BWT_PERIOD_PENDING)) return;
+    const uint32_t n = len[b];
+    const uint32_t tile0 = blockIdx.x * EW_TILE;
+    if (tile0 >= n) return;
+    const uint32_t di   = v & ~BWT_PERIOD_PENDING;
+    const uint32_t d    = div_vals[div_off[b] + di];
+    const uint8_t* T    = in + (uint64_t) b * stride;
+    const uint32_t tend = min(n, tile0 + EW_TILE);
+    bool           mism = false;
+    for (uint32_t i = tile0 + threadIdx.x; i < tend; i += 256)
+    {
+        uint32_t j = i + d;
+        if (j >= n) j -= n;
+        mism |= T[i] != T[j];
+    }
+    if (__syncthreads_or(mism) && threadIdx.x == 0) bad[(uint64_t) b * bad_stride + di] = 1;
+}
+
+__global__ void bwt_period_advance_kernel(const uint32_t* __restrict__ len, const uint32_t* __restrict__ div_vals, const uint32_t* __restrict__ div_off,
+                                          const uint32_t* __restrict__ div_cnt, const uint8_t* __restrict__ bad, uint32_t bad_stride,
+                                          uint32_t* __restrict__ period, uint32_t* __restrict__ pending, uint32_t nblk)
 {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk) return;
-    uint32_t p = len[b];
-    for (uint32_t di = 0; di < div_cnt[b]; ++di)
-        if (!bad[(uint64_t) b * bad_stride + di])
-        {
-            p = div_vals[div_off[b] + di];  // divisors are ascending: first survivor is the smallest period
-            break;
-        }
-    period[b] = p;
+    const uint32_t v = period[b];
+    if (!(v & BWT_PERIOD_PENDING)) return;
+    uint32_t di = v & ~BWT_PERIOD_PENDING;
+    if (!bad[(uint64_t) b * bad_stride + di])
+    {
+        period[b] = div_vals[div_off[b] + di];  // the candidate held everywhere: it is the smallest period
+        return;
+    }
+    const uint32_t cnt = div_cnt[b];
+    for (++di; di < cnt && bad[(uint64_t) b * bad_stride + di]; ++di) {}
+    if (di == cnt)
+        period[b] = len[b];
+    else
+    {
+        period[b] = BWT_PERIOD_PENDING | di;
+        atomicAdd(pending, 1u);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -985,9 +1026,9 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             // the pageable-host staging vectors die at scope exit: the copies above must have landed
             BRA_CUDA_TRY(cudaStreamSynchronize(st));
         }
-        BRA_LAUNCH(P_BWT_PERIOD, st, bwt_period_kernel<<<grid, 256, 0, st>>>(a.d_in, a.stride, a.d_len, a.d_div_vals, a.d_div_off, a.d_div_cnt, a.d_bad, a.bad_stride));
-        BRA_LAUNCH(P_BWT_PERIOD, st, bwt_period_select_kernel<<<bra_div_up(nblk, 128), 128, 0, st>>>(a.d_len, a.d_div_vals, a.d_div_off, a.d_div_cnt, a.d_bad,
-                                                                       a.bad_stride, a.d_period, nblk));
+        BRA_CUDA_TRY(cudaMemsetAsync(a.d_notdone, 0, 16, st));  // [0] alphabet bits (below), [1] blocks with a period candidate left
+        BRA_LAUNCH(P_BWT_PERIOD, st, bwt_period_pretest_kernel<<<nblk, 32, 0, st>>>(a.d_in, a.stride, a.d_len, a.d_div_vals, a.d_div_off, a.d_div_cnt, a.d_bad, a.bad_stride,
+                                                                                 a.d_period, a.d_notdone + 1));
     }
 
     BRA_CUDA_TRY(cudaMemsetAsync(a.d_done, 0, nblk, st));
@@ -1002,22 +1043,39 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     if (a.d_alpha && !no_alpha)
     {
         BRA_CUDA_TRY(cudaMemsetAsync(a.d_alpha, 0, (size_t) nblk * 256, st));
-        BRA_CUDA_TRY(cudaMemsetAsync(a.d_notdone, 0, 8, st));
         BRA_LAUNCH(P_BWT_KEYS, st, bwt_alpha_present_kernel<<<grid, 256, 0, st>>>(a.d_in, a.stride, a.d_len, a.d_alpha));
         BRA_LAUNCH(P_BWT_KEYS, st, bwt_alpha_codes_kernel<<<nblk, 256, 0, st>>>(a.d_alpha, a.d_notdone));
+    }
+    // one round trip for the alphabet width and the number of blocks whose period is still open; blocks with a surviving
+    // candidate divisor (periodic inputs only) then run full comparisons, one candidate per round
+    for (uint32_t round = 0;; ++round)
+    {
+        uint32_t st2[2] = {0, 0};
         if (a.h_mail)
         {
-            if (!mail_publish(a.h_mail, a.d_notdone, 1, st)) return false;
+            if (!mail_publish(a.h_mail, a.d_notdone, 2, st)) return false;
             BRA_CUDA_TRY(cudaStreamSynchronize(st));
-            cbits = *reinterpret_cast<volatile uint32_t*>(a.h_mail);
+            st2[0] = reinterpret_cast<volatile uint32_t*>(a.h_mail)[0];
+            st2[1] = reinterpret_cast<volatile uint32_t*>(a.h_mail)[1];
         }
         else
         {
-            BRA_CUDA_TRY(cudaMemcpyAsync(&cbits, a.d_notdone, 4, cudaMemcpyDeviceToHost, st));
+            BRA_CUDA_TRY(cudaMemcpyAsync(st2, a.d_notdone, 8, cudaMemcpyDeviceToHost, st));
             BRA_CUDA_TRY(cudaStreamSynchronize(st));
         }
-        if (cbits < 1 || cbits > 8) cbits = 8;
+        if (round == 0 && a.d_alpha && !no_alpha) cbits = st2[0];
+        if (st2[1] == 0) break;
+        if (round > a.bad_stride)
+        {
+            bra_b200_log_error("bwt: period detection did not settle");
+            return false;
+        }
+        BRA_CUDA_TRY(cudaMemsetAsync(a.d_notdone + 1, 0, 4, st));
+        BRA_LAUNCH(P_BWT_PERIOD, st, bwt_period_full_kernel<<<grid, 256, 0, st>>>(a.d_in, a.stride, a.d_len, a.d_div_vals, a.d_div_off, a.d_period, a.d_bad, a.bad_stride));
+        BRA_LAUNCH(P_BWT_PERIOD, st, bwt_period_advance_kernel<<<bra_div_up(nblk, 128), 128, 0, st>>>(a.d_len, a.d_div_vals, a.d_div_off, a.d_div_cnt, a.d_bad, a.bad_stride,
+                                                                                               a.d_period, a.d_notdone + 1, nblk));
     }
+    if (cbits < 1 || cbits > 8) cbits = 8;
     const size_t   ghist_bytes = (size_t) nblk * RS_GHIST_STRIDE * sizeof(uint32_t);
     const uint32_t init_passes = (4 * cbits + 7) / 8;
     BRA_CUDA_TRY(cudaMemsetAsync(a.d_hist, 0, ghist_bytes, st));
@@ -1406,13 +1464,39 @@ __global__ void __launch_bounds__(IB_THREADS)
     }
     else
     {
+        // periodic block: the walkers of the primary row's cycle write its q bytes once; ibwt_replicate_kernel repeats them
         for (uint32_t t = 0; t < steps; ++t)
         {
             const uint32_t e = Wb[idx];
-            for (uint32_t pos = o0 + t; pos < n; pos += q) ob[pos] = (uint8_t) e;
+            if (o0 + t < n) ob[o0 + t] = (uint8_t) e;
             idx = e >> 8;
         }
     }
+}
+
+// Periodic blocks (orbit q shorter than n): out[i] = out[i mod q] for i >= q, sixteen bytes per thread.
+__global__ void __launch_bounds__(256)
+    ibwt_replicate_kernel(const uint32_t* __restrict__ len, uint64_t stride, const uint32_t* __restrict__ orbit, uint8_t* __restrict__ out)
+{
+    const uint32_t b = blockIdx.y;
+    const uint32_t n = len[b], q = orbit[b];
+    if (q == 0 || q >= n) return;
+    uint8_t*       ob = out + (uint64_t) b * stride;
+    const uint64_t i0 = (uint64_t) q + ((uint64_t) blockIdx.x * 256 + threadIdx.x) * 16;
+    if (i0 >= n) return;
+    const uint32_t m = (uint32_t) min((uint64_t) 16, (uint64_t) n - i0);
+    uint32_t       x = (uint32_t) (i0 % q);
+    uint32_t       w[4] = {0, 0, 0, 0};
+    for (uint32_t k = 0; k < m; ++k)
+    {
+        w[k >> 2] |= (uint32_t) ob[x] << ((k & 3u) * 8u);
+        if (++x == q) x = 0;
+    }
+    uint8_t* dst = ob + i0;
+    if (m == 16 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0)
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    else
+        for (uint32_t k = 0; k < m; ++k) dst[k] = (uint8_t) (w[k >> 2] >> ((k & 3u) * 8u));
 }
 
 uint32_t ibwt_row_stride(uint32_t max_n)
@@ -1440,6 +1524,7 @@ static bool bwt_inverse_chunk(const BwtInvArgs& a, cudaStream_t st)
     if (cap)
         BRA_LAUNCH(P_IBWT_COPY, st, ibwt_copy_kernel<<<dim3(bra_div_up(kmax, 256), a.nblk), 256, 0, st>>>(a.d_len, a.stride, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_tmp, cap, a.d_out, ovf));
     BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_walk_emit_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_out, cap, ovf));
+    BRA_LAUNCH(P_IBWT_WALK_EMIT, st, ibwt_replicate_kernel<<<dim3(bra_div_up(a.max_n, 4096), a.nblk), 256, 0, st>>>(a.d_len, a.stride, a.d_orbit, a.d_out));
     BRA_CUDA_TRY(cudaGetLastError());
     return true;
 }
