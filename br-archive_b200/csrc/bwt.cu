@@ -805,7 +805,7 @@ __global__ void __launch_bounds__(EW_THREADS, 4)
 // only (a group spanning a border counts as two pieces -- the decision it feeds is a cost heuristic, not a correctness
 // condition, and a tile without any head still reports a piece of 4096).
 template <int KIND>
-__global__ void __launch_bounds__(EW_THREADS)
+__global__ void __launch_bounds__(EW_THREADS, 4)
     bwt_heads_stats_kernel(const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo, uint64_t stride, const uint32_t* __restrict__ period,
                            const uint8_t* __restrict__ skip, uint8_t* __restrict__ flags, uint32_t* __restrict__ sa_out, int* __restrict__ tile_last,
                            uint32_t tiles, uint32_t* __restrict__ ngroups, uint32_t* __restrict__ tile_heads, uint32_t* __restrict__ maxgroup,

@@ -92,6 +92,14 @@ def test_bwt_shapes_vs_oracle(dropin, oracle, pkg, vocab):
     cases.append(b"ab" * 5000 + b"c")
     cases.append(bytes(40000))
     cases.append(b"abc" * 4096 * 3)
+    # period candidates: divisors that survive the 32-byte pretest and are refuted (or not) by the full comparison, one
+    # after the other -- smallest true period 48 behind false candidates 1..24, a defect in the last byte (no period at
+    # all although every divisor >= 32 passes the pretest), a defect in the middle, and period 6 of n = 6 * 2048
+    cases.append((b"x" * 40 + b"yzyzyzyz") * 256)
+    cases.append(b"q" * 12287 + b"r")
+    cases.append(b"ab" * 3000 + b"aa" + b"ab" * 3143)
+    cases.append(b"abcabd" * 2048)
+    cases.append((b"0123456789abcdef" * 4 + b"0123456789abcdeX") * 96)  # period 80 hidden behind the pretest-period 16
     for d in cases:
         exp = oracle.bwt_encode(d)
         got = dropin.bwt_encode2(d)
