@@ -17,7 +17,8 @@
 // INVERSE (replaces reference bra_bwt_decode2, bra_bwt.c:133-168)
 //   transform[] is the stable sort of positions by byte value = one 8-bit radix pass, emitted
 //   as W[j] = transform[j] << 8 | F[j] so that the chase needs one load per output byte. The
-//   n-step dependent chase is cut into ~n/R independent walks that start at every R-th row
+//   n-step dependent chase is cut into ~n/R independent walks (16384 per block: twice the walkers halve the blocks whose W
+//   arrays are in flight at once, and with them the DRAM sectors fetched per step) that start at every R-th row
 //   (and at the primary row) and stop at the next start row; a per-block stitch orders the
 //   walks from the primary row and a second walk writes the bytes at their final offsets.
 #include "bra_common.cuh"
@@ -1361,11 +1362,12 @@ __global__ void __launch_bounds__(256)
 // log2(K) rounds over all walkers) instead of following the chain link by link.
 #define IB_STITCH_THREADS 256
 #define IB_TERM 0xFFFFFFFFu
+#define IB_TERM16 0xFFFFu  // (walker indices stay below 65535: ibwt_kmax)
 __global__ void __launch_bounds__(IB_STITCH_THREADS)
     ibwt_stitch_kernel(const uint32_t* __restrict__ len, const uint32_t* __restrict__ primary, uint32_t R, uint32_t kmax,
                        const uint2* __restrict__ walk, uint32_t* __restrict__ woff, uint32_t* __restrict__ orbit, const uint32_t* __restrict__ ovf)
 {
-    extern __shared__ uint32_t s_dyn[];  // two (distance to the end of the cycle, link) pairs of kmax words each, ping-pong
+    extern __shared__ uint32_t s_dyn[];  // two (distance to the end of the cycle: u32, link: u16) pairs of kmax entries each, ping-pong
     const uint32_t b = blockIdx.x;
     const uint32_t n = len[b];
     if (n == 0)
@@ -1375,12 +1377,14 @@ __global__ void __launch_bounds__(IB_STITCH_THREADS)
     }
     const uint32_t K  = ib_rows(n, R);
     const uint32_t NW = ib_walkers(K, ovf, b, kmax);  // walkers 0..NW-1 (K is the primary row's, the ones behind it are overflow walkers)
-    uint32_t*      d0 = s_dyn, *n0 = s_dyn + kmax, *d1 = s_dyn + 2 * kmax, *n1 = s_dyn + 3 * kmax;
+    const uint32_t kp = (kmax + 1u) & ~1u;            // (keeps the u16 arrays behind the u32 ones 4-byte aligned)
+    uint32_t *     d0 = s_dyn, *d1 = s_dyn + kp;
+    uint16_t *     n0 = reinterpret_cast<uint16_t*>(s_dyn + 2 * kp), *n1 = n0 + kp;
     for (uint32_t w = threadIdx.x; w < NW; w += IB_STITCH_THREADS)
     {
         const uint2 e = walk[(uint64_t) b * kmax + w];
         d0[w]         = e.x;
-        n0[w]         = e.y == K ? IB_TERM : e.y;  // the cycle is cut where it returns to K
+        n0[w]         = e.y == K ? (uint16_t) IB_TERM16 : (uint16_t) e.y;  // the cycle is cut where it returns to K
     }
     __syncthreads();
     for (uint32_t span = 1;;)  // links every pointer has jumped so far
@@ -1389,18 +1393,18 @@ __global__ void __launch_bounds__(IB_STITCH_THREADS)
         for (uint32_t w = threadIdx.x; w < NW; w += IB_STITCH_THREADS)
         {
             const uint32_t nx = n0[w];
-            uint32_t       dd = d0[w], nn = IB_TERM;
-            if (nx != IB_TERM)
+            uint32_t       dd = d0[w], nn = IB_TERM16;
+            if (nx != IB_TERM16)
             {
                 dd += d0[nx];  // wraps for walkers that are not on K's cycle; they are discarded below
                 nn   = n0[nx];
                 open = true;
             }
             d1[w] = dd;
-            n1[w] = nn;
+            n1[w] = (uint16_t) nn;
         }
         uint32_t* t = d0; d0 = d1; d1 = t;
-        t = n0; n0 = n1; n1 = t;
+        uint16_t* u = n0; n0 = n1; n1 = u;
         const bool any = __syncthreads_or(open);
         span <<= 1;
         // a walker on K's cycle is at most NW links from the cut; walkers on other cycles never reach it
@@ -1411,7 +1415,7 @@ __global__ void __launch_bounds__(IB_STITCH_THREADS)
     for (uint32_t w = threadIdx.x; w < NW; w += IB_STITCH_THREADS)
     {
         uint32_t off = IB_INVALID;
-        if (n0[w] == IB_TERM && !(w != K && pi % R == 0 && w == pi / R)) off = q - d0[w];  // a start row equal to the primary row is walker K's double
+        if (n0[w] == IB_TERM16 && !(w != K && pi % R == 0 && w == pi / R)) off = q - d0[w];  // a start row equal to the primary row is walker K's double
         woff[(uint64_t) b * kmax + w] = off;
     }
     if (threadIdx.x == 0) orbit[b] = q;
@@ -1501,8 +1505,9 @@ __global__ void __launch_bounds__(256)
 
 uint32_t ibwt_row_stride(uint32_t max_n)
 {
-    uint32_t R = 128;
-    while ((uint64_t) R * 8192 < max_n) R *= 2;
+    static const uint32_t max_walkers = getenv("BRA_B200_IBWT_WALKERS") ? (uint32_t) atoi(getenv("BRA_B200_IBWT_WALKERS")) : 16384u;  // tuning switch (8192 or 16384), read once
+    uint32_t R = 64;
+    while ((uint64_t) R * max_walkers < max_n) R *= 2;
     return R;
 }
 uint32_t ibwt_tmp_cap(uint32_t max_n) { return 8u * ibwt_row_stride(max_n); }
@@ -1518,8 +1523,8 @@ static bool bwt_inverse_chunk(const BwtInvArgs& a, cudaStream_t st)
     uint32_t* ovf = (a.d_tmp && a.d_ovf) ? a.d_ovf : nullptr;
     if (ovf) BRA_CUDA_TRY(cudaMemsetAsync(ovf, 0, (size_t) a.nblk * (IB_OVF + 1u) * sizeof(uint32_t), st));
     BRA_LAUNCH(P_IBWT_WALK_LEN, st, ibwt_walk_len_kernel<<<grid, IB_THREADS, 0, st>>>(a.d_W, a.stride, a.d_len, a.d_primary, R, kmax, a.d_walk, ovf, a.d_tmp, cap));
-    const size_t stitch_smem = (size_t) kmax * 4 * sizeof(uint32_t);
-    BRA_CUDA_TRY(cudaFuncSetAttribute(ibwt_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 8300 * 4));
+    const size_t stitch_smem = (size_t) ((kmax + 1u) & ~1u) * 2 * (sizeof(uint32_t) + sizeof(uint16_t));
+    BRA_CUDA_TRY(cudaFuncSetAttribute(ibwt_stitch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) stitch_smem));
     BRA_LAUNCH(P_IBWT_STITCH, st, ibwt_stitch_kernel<<<a.nblk, IB_STITCH_THREADS, stitch_smem, st>>>(a.d_len, a.d_primary, R, kmax, a.d_walk, a.d_woff, a.d_orbit, ovf));
     if (cap)
         BRA_LAUNCH(P_IBWT_COPY, st, ibwt_copy_kernel<<<dim3(bra_div_up(kmax, 256), a.nblk), 256, 0, st>>>(a.d_len, a.stride, R, kmax, a.d_walk, a.d_woff, a.d_orbit, a.d_tmp, cap, a.d_out, ovf));
