@@ -1505,7 +1505,8 @@ __global__ void __launch_bounds__(256)
 
 uint32_t ibwt_row_stride(uint32_t max_n)
 {
-    static const uint32_t max_walkers = getenv("BRA_B200_IBWT_WALKERS") ? (uint32_t) atoi(getenv("BRA_B200_IBWT_WALKERS")) : 16384u;  // tuning switch (8192 or 16384), read once
+    static const uint32_t max_walkers =  // tuning switch, read once; the stitch kernel holds 12 bytes per walker in shared memory and links them in 16 bits
+        getenv("BRA_B200_IBWT_WALKERS") ? (uint32_t) std::min(16384, std::max(1024, atoi(getenv("BRA_B200_IBWT_WALKERS")))) : 16384u;
     uint32_t R = 64;
     while ((uint64_t) R * max_walkers < max_n) R *= 2;
     return R;

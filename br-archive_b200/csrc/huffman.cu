@@ -301,6 +301,13 @@ struct HdShared
 // fast the code re-synchronises (near-uniform code lengths, i.e. incompressible data, hardly ever do).
 #define HD_PHASE_MAX 12u
 #define HD_PHASE_SEQ_BYTES (HD_PHASE_MAX * HD_THREADS * 3u + 16u)  // per sequence: exits u8 [phase][sub], counts u16 [phase][sub], exit map of the sequence
+// Phase mode is for codes that hardly ever re-synchronise: short and of nearly uniform length (incompressible data: 7 to 9
+// bits). A code with short and long words (compressible data) re-synchronises within a few words, and walking every
+// phase would cost several times the fixed-point iteration.
+__host__ __device__ __forceinline__ bool hd_phase_mode(uint32_t min_len, uint32_t max_len)
+{
+    return max_len >= 1 && max_len <= HD_PHASE_MAX && max_len - min_len <= 3;
+}
 struct HdSyncShared
 {
     HdShared S;
@@ -445,7 +452,7 @@ __global__ void __launch_bounds__(HD_THREADS)
     const uint32_t data_end = min((uint32_t) HD_SEQ_BITS + 64u, (c - seq * HD_SEQ_BYTES) * 8u);  // relative bit where the payload ends
     __syncthreads();
     const uint32_t L = S.tab.max_len;
-    if (phase_ws && L >= 1 && L <= HD_PHASE_MAX && entry < L)
+    if (phase_ws && hd_phase_mode(S.tab.min_len, L) && entry < L)
     {
         uint8_t*  g_pe  = phase_ws + sidx * HD_PHASE_SEQ_BYTES;
         uint16_t* g_pc  = reinterpret_cast<uint16_t*>(g_pe + HD_PHASE_MAX * HD_THREADS);
@@ -590,7 +597,7 @@ __global__ void huf_dec_phase_chain_kernel(const uint32_t* __restrict__ clen, co
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblk || err[b]) return;
     const uint32_t L = tabs[b].max_len;
-    if (L < 1 || L > HD_PHASE_MAX) return;
+    if (!hd_phase_mode(tabs[b].min_len, L)) return;
     const uint32_t nseq = (clen[b] + HD_SEQ_BYTES - 1) / HD_SEQ_BYTES;
     uint32_t       ph   = 0;
     for (uint32_t s = 0; s < nseq; ++s)

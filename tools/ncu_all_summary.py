@@ -56,7 +56,7 @@ def main():
     print(f"total kernel time {total:.3f} ms over {sum(int(a['n']) for a in agg.values())} launches (cold-cache, serialised; shares are what compares with the live brackets)")
     if len(sys.argv) > 3 and sys.argv[2] == "--traffic":
         # DRAM bytes per element of the FULL-BATCH launches only (the end-to-end stages of the same run launch the same
-        # kernels on fewer blocks): per family, the launches lasting at least 80 % of the family's longest one
+        # kernels on fewer blocks): per family, the launches lasting at least 93 % of the family's longest one
         elems = float(sys.argv[3])
         fam = defaultdict(list)
         for (_, name), m in launches.items():
@@ -68,7 +68,7 @@ def main():
         out = {}
         for f, rows in sorted(fam.items()):
             gmax = max(g for g, _ in rows)
-            full = [b for g, b in rows if g >= 0.8 * gmax]
+            full = [b for g, b in rows if g >= 0.93 * gmax]
             out[f] = round(sum(full) / len(full) / elems, 2)
         print(json.dumps(out, indent=1))
 
