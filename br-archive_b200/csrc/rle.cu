@@ -16,9 +16,10 @@
 //   heads -> literal flags -> sizes + emit (+ the 256-bin histogram Huffman needs; output offsets by look-back).
 //
 // DECODE. Token boundaries depend on all previous tokens. Per 1 KiB tile the map "entry offset
-// -> exit offset" is built for every possible entry (a token overhangs by at most 128 bytes)
-// by pointer doubling in shared memory; one thread per block chains the tiles; tiles then mark
-// their true token starts the same way, count, and expand with a binary search per output byte.
+// -> exit offset" is built for every possible entry (a token overhangs by at most 128 bytes):
+// one warp walks the token path from entry 0, the paths from the other entries are followed until
+// they merge with it; one warp per block chains the tiles; tiles then mark their true token
+// starts by the same warp walk, count, and expand with a binary search per output byte.
 #include "bra_common.cuh"
 #include "bra_kernels.h"
 
@@ -427,50 +428,80 @@ __device__ __forceinline__ uint32_t rle_tok_out(uint8_t c)  // bytes of output i
     return s >= 0 ? (uint32_t) s + 1u : (s == -128 ? 0u : (uint32_t) (1 - s));
 }
 
-// Builds J[i] = first position >= tile_n reached from i (absolute exit), in shared memory, by pointer doubling.
-// The loop stops as soon as every pointer is terminal: ceil(log2(tokens per tile)) + 1 rounds -- 3-4 on
-// literal-heavy data, up to 10 when the tile is all one-byte tokens. Returns the buffer holding the result.
-__device__ __forceinline__ uint16_t* rle_dec_jump_closure(const uint8_t* __restrict__ xb, uint32_t tile0, uint32_t tile_n, uint16_t* Ja, uint16_t* Jb)
+// The token path through a tile, one WARP per tile. The lanes look at 32 consecutive positions at a time (their control
+// bytes and token lengths); the path inside the window is then followed by shuffles -- position -> position + length of
+// the token there -- which costs a couple of instructions per token for the whole warp. `pos` is uniform over the warp.
+#define RD_WARPS 8  // tiles per CTA
+__device__ __forceinline__ void rle_dec_stage_tile(const uint8_t* __restrict__ xb, uint32_t tile0, uint32_t tile_n, uint8_t* sx)
 {
-    for (uint32_t i = threadIdx.x; i < RD_TILE; i += RD_THREADS)
-        Ja[i] = i < tile_n ? (uint16_t) (i + rle_tok_len(xb[tile0 + i])) : (uint16_t) i;
-    __syncthreads();
-    uint16_t *src = Ja, *dst = Jb;
-    for (int r = 0; r < 10; ++r)
+    const uint32_t l = lane_id();
+    if (tile_n == RD_TILE && ((reinterpret_cast<uintptr_t>(xb) + tile0) & 15u) == 0)
     {
-        bool open = false;
-        for (uint32_t i = threadIdx.x; i < RD_TILE; i += RD_THREADS)
-        {
-            const uint16_t j = src[i];
-            const uint16_t n = j < tile_n ? src[j] : j;
-            dst[i]           = n;
-            open |= n < tile_n;
-        }
-        uint16_t* tmp = src;
-        src           = dst;
-        dst           = tmp;
-        if (!__syncthreads_or(open)) break;
+        const uint4* q = reinterpret_cast<const uint4*>(xb + tile0);
+        reinterpret_cast<uint4*>(sx)[l]      = q[l];
+        reinterpret_cast<uint4*>(sx)[l + 32] = q[l + 32];
     }
-    return src;
+    else
+        for (uint32_t i = l; i < RD_TILE; i += 32) sx[i] = i < tile_n ? xb[tile0 + i] : 0;
+    __syncwarp();
 }
 
-__global__ void __launch_bounds__(RD_THREADS)
+// Exit offsets of a tile for every possible entry (a token starting in the previous tile overhangs by 0..129 bytes): the
+// path from entry 0 is walked and marked; the path from any other entry is followed only until it meets a marked
+// position -- from there on the two paths are one -- or leaves the tile. RLE streams re-synchronise within a few tokens,
+// so the other 129 walks are short (and never longer than the tile has tokens).
+__global__ void __launch_bounds__(RD_WARPS * 32)
     rle_dec_exit_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ rlen, uint32_t tiles,
                         uint8_t* __restrict__ t_exit /* [b][tile][RD_ENTRIES] */)
 {
-    __shared__ uint16_t Ja[RD_TILE], Jb[RD_TILE];
-    const uint32_t      b = blockIdx.y, t = blockIdx.x;
-    const uint32_t      r = rlen[b];
-    const uint32_t      tile0 = t * RD_TILE;
-    if (tile0 >= r) return;
+    __shared__ __align__(16) uint8_t s_x[RD_WARPS][RD_TILE];
+    __shared__ uint32_t              s_mark[RD_WARPS][RD_TILE / 32];
+    const uint32_t b = blockIdx.y, w = warp_id(), l = lane_id();
+    const uint32_t t = blockIdx.x * RD_WARPS + w;
+    const uint32_t r = rlen[b];
+    const uint32_t tile0 = t * RD_TILE;
+    if (tile0 >= r) return;  // whole warps leave; no CTA barrier below
     const uint32_t tile_n = min((uint32_t) RD_TILE, r - tile0);
-    const uint16_t* J = rle_dec_jump_closure(in + (uint64_t) b * stride, tile0, tile_n, Ja, Jb);
-    if (threadIdx.x < RD_ENTRIES)
+    uint8_t*       sx     = s_x[w];
+    rle_dec_stage_tile(in + (uint64_t) b * stride, tile0, tile_n, sx);
+    uint32_t pos = 0;
+    for (uint32_t win = 0; win < RD_TILE / 32; ++win)
     {
-        // entries beyond the tile (only possible in a short last tile) are never followed
-        const uint32_t e = threadIdx.x;
-        const uint32_t x = e < tile_n ? (uint32_t) J[e] - tile_n : 0u;
-        t_exit[((uint64_t) b * tiles + t) * RD_ENTRIES + e] = (uint8_t) min(x, 255u);
+        const uint32_t wb  = win * 32;
+        const uint32_t len = rle_tok_len(sx[wb + l]);
+        uint32_t       m   = 0;
+        while (pos < wb + 32 && pos < tile_n)
+        {
+            m |= 1u << (pos - wb);
+            pos += __shfl_sync(BRA_FULL, len, pos - wb);
+        }
+        if (l == 0) s_mark[w][win] = m;
+    }
+    __syncwarp();
+    const uint32_t exit0 = pos - tile_n;  // pos >= tile_n here
+    uint8_t*       ex    = t_exit + ((uint64_t) b * tiles + t) * RD_ENTRIES;
+    for (uint32_t e = l; e < RD_ENTRIES; e += 32)
+    {
+        uint32_t x = 0;  // entries beyond the tile (only possible in a short last tile) are never followed
+        if (e < tile_n)
+        {
+            uint32_t p = e;
+            for (;;)
+            {
+                if (p >= tile_n)
+                {
+                    x = p - tile_n;
+                    break;
+                }
+                if ((s_mark[w][p >> 5] >> (p & 31u)) & 1u)
+                {
+                    x = exit0;
+                    break;
+                }
+                p += rle_tok_len(sx[p]);
+            }
+        }
+        ex[e] = (uint8_t) min(x, 255u);
     }
 }
 
@@ -521,65 +552,45 @@ __global__ void __launch_bounds__(32) rle_dec_chain_kernel(const uint32_t* __res
     }
 }
 
-__global__ void __launch_bounds__(RD_THREADS)
+// True token starts of a tile (bitmap) and its output size, from the tile's entry offset: the same warp walk.
+__global__ void __launch_bounds__(RD_WARPS * 32)
     rle_dec_mark_kernel(const uint8_t* __restrict__ in, uint64_t stride, const uint32_t* __restrict__ rlen, uint32_t tiles,
                         const uint8_t* __restrict__ t_entry, uint32_t* __restrict__ t_tok /* [b][tile][32] */, uint32_t* __restrict__ t_ocnt,
                         uint32_t* __restrict__ err)
 {
-    __shared__ uint16_t Ja[RD_TILE], Jb[RD_TILE];
-    __shared__ uint8_t  reach[RD_TILE];
-    __shared__ uint32_t ured[34];
-    const uint32_t      b = blockIdx.y, t = blockIdx.x;
-    const uint32_t      r = rlen[b];
-    const uint32_t      tile0 = t * RD_TILE;
-    if (tile0 >= r) return;
+    __shared__ __align__(16) uint8_t s_x[RD_WARPS][RD_TILE];
+    const uint32_t b = blockIdx.y, w = warp_id(), l = lane_id();
+    const uint32_t t = blockIdx.x * RD_WARPS + w;
+    const uint32_t r = rlen[b];
+    const uint32_t tile0 = t * RD_TILE;
+    if (tile0 >= r) return;  // whole warps leave; no CTA barrier below
     const uint32_t tile_n = min((uint32_t) RD_TILE, r - tile0);
-    const uint8_t* xb     = in + (uint64_t) b * stride;
-    const uint32_t entry  = t_entry[(uint64_t) b * tiles + t];
-
-    for (uint32_t i = threadIdx.x; i < RD_TILE; i += RD_THREADS)
+    uint8_t*       sx     = s_x[w];
+    rle_dec_stage_tile(in + (uint64_t) b * stride, tile0, tile_n, sx);
+    uint32_t pos = t_entry[(uint64_t) b * tiles + t], total = 0;
+    bool     bad = false;
+    uint32_t* tok = t_tok + ((uint64_t) b * tiles + t) * 32;
+    for (uint32_t win = 0; win < RD_TILE / 32; ++win)
     {
-        Ja[i]    = i < tile_n ? (uint16_t) (i + rle_tok_len(xb[tile0 + i])) : (uint16_t) i;
-        reach[i] = (i == entry && i < tile_n);
-    }
-    __syncthreads();
-    uint16_t *src = Ja, *dst = Jb;
-    for (int rd = 0; rd < 10; ++rd)
-    {
-        bool open = false;
-        for (uint32_t i = threadIdx.x; i < RD_TILE; i += RD_THREADS)
+        const uint32_t wb  = win * 32;
+        const uint8_t  c   = sx[wb + l];
+        const uint32_t len = rle_tok_len(c), out = rle_tok_out(c);
+        uint32_t       m   = 0;
+        while (pos < wb + 32 && pos < tile_n)
         {
-            const uint16_t j = src[i];
-            if (reach[i] && j < tile_n) reach[j] = 1;  // J^(2^rd) of a reachable start is reachable
-            const uint16_t n = j < tile_n ? src[j] : j;
-            dst[i]           = n;
-            open |= j < tile_n;  // this round still had a live pointer to follow
+            const uint32_t k = pos - wb;
+            m |= 1u << k;
+            total += __shfl_sync(BRA_FULL, out, k);
+            pos += __shfl_sync(BRA_FULL, len, k);
+            bad |= (uint64_t) tile0 + pos > r;  // truncated token: the reference's error exits (bra_rle.c:136,148)
         }
-        uint16_t* tmp = src;
-        src           = dst;
-        dst           = tmp;
-        if (!__syncthreads_or(open)) break;
+        if (l == 0) tok[win] = m;
     }
-    // token bitmap + output count; truncated tokens are the reference's error exits (bra_rle.c:136,148)
-    uint32_t mycnt = 0;
-    bool     bad   = false;
-    for (uint32_t k = 0; k < RD_TILE / RD_THREADS; ++k)
+    if (l == 0)
     {
-        const uint32_t i    = k * RD_THREADS + threadIdx.x;
-        const bool     tok  = i < tile_n && reach[i];
-        const uint32_t ball = __ballot_sync(BRA_FULL, tok);
-        if (lane_id() == 0) t_tok[((uint64_t) b * tiles + t) * 32 + (i >> 5)] = ball;
-        if (tok)
-        {
-            const uint8_t c = xb[tile0 + i];
-            mycnt += rle_tok_out(c);
-            if ((uint64_t) tile0 + i + rle_tok_len(c) > r) bad = true;
-        }
+        t_ocnt[(uint64_t) b * tiles + t] = total;
+        if (bad) err[b] = 1;
     }
-    uint32_t total;
-    block_excl_add(mycnt, ured, &total);
-    if (threadIdx.x == 0) t_ocnt[(uint64_t) b * tiles + t] = total;
-    if (bad) err[b] = 1;
 }
 
 __global__ void __launch_bounds__(RD_THREADS)
@@ -676,9 +687,10 @@ bool rle_decode_batch(const RleDecArgs& a, cudaStream_t st)
     if (a.nblk == 0 || a.max_r == 0) return true;
     const uint32_t tiles = bra_div_up(a.max_r, RD_TILE);
     const dim3     grid(tiles, a.nblk);
-    BRA_LAUNCH(P_RLE_DEC_EXIT, st, rle_dec_exit_kernel<<<grid, RD_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_exit));
+    const dim3 wgrid(bra_div_up(tiles, RD_WARPS), a.nblk);  // one warp per tile
+    BRA_LAUNCH(P_RLE_DEC_EXIT, st, rle_dec_exit_kernel<<<wgrid, RD_WARPS * 32, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_exit));
     BRA_LAUNCH(P_RLE_DEC_CHAIN, st, rle_dec_chain_kernel<<<a.nblk, 32, 0, st>>>(a.d_rlen, tiles, a.d_t_exit, a.d_t_entry, a.nblk));
-    BRA_LAUNCH(P_RLE_DEC_MARK, st, rle_dec_mark_kernel<<<grid, RD_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_entry, a.d_t_tok, a.d_t_ocnt, a.d_err));
+    BRA_LAUNCH(P_RLE_DEC_MARK, st, rle_dec_mark_kernel<<<wgrid, RD_WARPS * 32, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_entry, a.d_t_tok, a.d_t_ocnt, a.d_err));
     if (a.size_only)
         BRA_LAUNCH(P_RLE_DEC_EXPAND, st, rle_dec_expand_kernel<<<grid, RD_THREADS, 0, st>>>(a.d_in, a.stride, a.d_rlen, tiles, a.d_t_tok, a.d_t_ocnt, a.d_err, nullptr, 0, 0xFFFFFFFFu,
                                                            a.d_nlen));
