@@ -717,23 +717,35 @@ __global__ void __launch_bounds__(EW_THREADS)
     }
 }
 
-// ---- packed rounds (blocks of at most 2^21 bytes) -----------------------------------------------------------------------
+// ---- packed rounds (blocks of at most 2^21 bytes; up to 2^24 bytes while the group numbers fit 20 bits) -----------------------------------------------------------------------
 // A doubling round orders element v = SA[j] - h by (group of v, group of v + h). The second component is the group of
 // traversal slot j itself, i.e. the position of the last head at or before j -- known while the round's records are
 // written, no gather needed. With 21 bits per field the triple (key, second key, v) fits the 8 bytes per element the sort
 // moves anyway: hi = key << 11 | second >> 10, lo = (second & 1023) << 22 | v. After the sort, new heads are where
 // (key, second) differs from the left neighbour: a streaming pass instead of one more random gather per element.
 #define BWT_PACK_MAX_N (1u << 21)
-#define BWT_PACK_KEY_SHIFT 11u
 
 // Both kernels are warp-striped: warp w owns slots [512 w, 512 w + 512) of the tile and visits them in 16 rounds of 32
 // consecutive slots, so every load and store is one contiguous 128-byte (or 32-byte) piece per warp, and "last head at
 // or before slot j" is a ballot and a count-leading-zeros away.
+// Two layouts. WIDE == false (blocks up to 2 MiB): rotation in 22 bits, second key = position of the slot's group head
+// (21 bits), key up to 21 bits. WIDE == true (blocks up to 16 MiB, rounds on dense group numbers of at most 20 bits):
+// rotation in 24 bits, second key = NUMBER of the slot's group (20 bits), key up to 20 bits.
+template <bool WIDE>
+struct BwtPack
+{
+    static constexpr uint32_t VBITS = WIDE ? 24u : 22u;          // rotation index
+    static constexpr uint32_t RLO   = 32u - VBITS;               // low bits of the second key that share the word with it
+    static constexpr uint32_t KS    = (WIDE ? 20u : 21u) - RLO;  // the key starts at this bit of the high word
+};
+template <bool WIDE>
 __global__ void __launch_bounds__(EW_THREADS, 4)
     bwt_dbl_prepare_packed_kernel(const uint32_t* __restrict__ sa, const uint32_t* __restrict__ rank, const uint8_t* __restrict__ flags, uint32_t h,
                                   uint64_t stride, const uint32_t* __restrict__ period, const uint8_t* __restrict__ skip,
-                                  const int* __restrict__ tile_last, uint32_t tiles, uint32_t* __restrict__ hi_out, uint32_t* __restrict__ lo_out)
+                                  const int* __restrict__ tile_last, const uint32_t* __restrict__ tile_heads, uint32_t tiles,
+                                  uint32_t* __restrict__ hi_out, uint32_t* __restrict__ lo_out)
 {
+    using L = BwtPack<WIDE>;
     __shared__ int red[8], s_wl[8];
     const uint32_t b = blockIdx.y;
     if (skip[b]) return;
@@ -744,29 +756,42 @@ __global__ void __launch_bounds__(EW_THREADS, 4)
     const uint32_t hm   = h % p;
     const uint32_t w = warp_id(), l = lane_id();
     const uint32_t seg0 = tile0 + w * 512;
-    // last head of the warp's slots: one ballot per round
-    int wl = -1;
+    // WIDE: heads in the warp's slots (their count gives group numbers); else: the last head of the warp's slots
+    int wl = WIDE ? 0 : -1;
 #pragma unroll 4
     for (int r = 0; r < 16; ++r)
     {
         const uint32_t j  = seg0 + r * 32 + l;
         const uint32_t hb = __ballot_sync(BRA_FULL, j < p && flags[base + j] != 0);
-        if (hb) wl = (int) (seg0 + r * 32 + (31 - __clz(hb)));
+        if (WIDE)
+            wl += __popc(hb);
+        else if (hb)
+            wl = (int) (seg0 + r * 32 + (31 - __clz(hb)));
     }
-    // carry-in: last head before this tile, then before this warp's slots
+    // carry-in from the tiles before this one (head count / last head), then from the warps before me
     int carry = 0;
-    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += EW_THREADS) carry = max(carry, tile_last[(uint64_t) b * tiles + t]);
+    for (uint32_t t = threadIdx.x; t < blockIdx.x; t += EW_THREADS)
+    {
+        if (WIDE)
+            carry += (int) tile_heads[(uint64_t) b * tiles + t];
+        else
+            carry = max(carry, tile_last[(uint64_t) b * tiles + t]);
+    }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) carry = max(carry, __shfl_xor_sync(BRA_FULL, carry, d));
+    for (int d = 16; d > 0; d >>= 1)
+    {
+        const int o = __shfl_xor_sync(BRA_FULL, carry, d);
+        carry       = WIDE ? carry + o : max(carry, o);
+    }
     if (l == 0)
     {
         red[w]  = carry;
         s_wl[w] = wl;
     }
     __syncthreads();
-    int run = red[0];
-    for (int i = 1; i < 8; ++i) run = max(run, red[i]);
-    for (uint32_t i = 0; i < w; ++i) run = max(run, s_wl[i]);
+    int run = red[0];  // WIDE: heads before the current round; else: last head at or before it
+    for (int i = 1; i < 8; ++i) run = WIDE ? run + red[i] : max(run, red[i]);
+    for (uint32_t i = 0; i < w; ++i) run = WIDE ? run + s_wl[i] : max(run, s_wl[i]);
     // two halves of eight rounds: eight independent gathers per lane in flight, registers for four CTAs per SM
 #pragma unroll 1
     for (int half = 0; half < 2; ++half)
@@ -788,12 +813,21 @@ __global__ void __launch_bounds__(EW_THREADS, 4)
             const uint32_t j    = j0r + l;
             const uint32_t hb   = __ballot_sync(BRA_FULL, j < p && flags[base + j] != 0);
             const uint32_t mine = hb & (lanemask_lt() | (1u << l));
-            const uint32_t r2   = mine ? j0r + (31 - __clz(mine)) : (uint32_t) run;
-            if (hb) run = (int) (j0r + (31 - __clz(hb)));
+            uint32_t       r2;
+            if (WIDE)
+            {
+                r2 = (uint32_t) run + __popc(mine) - 1u;  // slot 0 is a head: at least one head at or before j
+                run += __popc(hb);
+            }
+            else
+            {
+                r2 = mine ? j0r + (31 - __clz(mine)) : (uint32_t) run;
+                if (hb) run = (int) (j0r + (31 - __clz(hb)));
+            }
             if (j < p)
             {
-                hi_out[base + j] = (k[r] << BWT_PACK_KEY_SHIFT) | (r2 >> 10);
-                lo_out[base + j] = ((r2 & 1023u) << 22) | v[r];
+                hi_out[base + j] = (k[r] << L::KS) | (r2 >> L::RLO);
+                lo_out[base + j] = ((r2 & ((1u << L::RLO) - 1u)) << L::VBITS) | v[r];
             }
         }
     }
@@ -810,7 +844,7 @@ __global__ void __launch_bounds__(EW_THREADS, 4)
     bwt_heads_stats_kernel(const uint32_t* __restrict__ hi, const uint32_t* __restrict__ lo, uint64_t stride, const uint32_t* __restrict__ period,
                            const uint8_t* __restrict__ skip, uint8_t* __restrict__ flags, uint32_t* __restrict__ sa_out, int* __restrict__ tile_last,
                            uint32_t tiles, uint32_t* __restrict__ ngroups, uint32_t* __restrict__ tile_heads, uint32_t* __restrict__ maxgroup,
-                           unsigned long long* __restrict__ sumsq)
+                           unsigned long long* __restrict__ sumsq, uint32_t vbits /* KIND 1: width of the rotation field */)
 {
     __shared__ int                s_first[8], s_last[8];
     __shared__ uint32_t           s_cnt[8], s_mg[8];
@@ -839,14 +873,14 @@ __global__ void __launch_bounds__(EW_THREADS, 4)
     if (seg0 > 0 && seg0 < p)
     {
         ph = hi[base + seg0 - 1];
-        if (KIND == 1) pl = lo[base + seg0 - 1] >> 22;
+        if (KIND == 1) pl = lo[base + seg0 - 1] >> vbits;
     }
 #pragma unroll
     for (int r = 0; r < 16; ++r)
     {
         const uint32_t j0r = seg0 + r * 32;
         const uint32_t j   = j0r + l;
-        const uint32_t s2  = xl[r] >> 22;
+        const uint32_t s2  = xl[r] >> vbits;
         uint32_t       lh = __shfl_up_sync(BRA_FULL, xh[r], 1), ll = __shfl_up_sync(BRA_FULL, s2, 1);
         if (l == 0)
         {
@@ -877,7 +911,7 @@ __global__ void __launch_bounds__(EW_THREADS, 4)
         if (j < p)
         {
             flags[base + j] = head ? 1 : 0;
-            if (KIND == 1) sa_out[base + j] = xl[r] & 0x3FFFFFu;
+            if (KIND == 1) sa_out[base + j] = xl[r] & ((1u << vbits) - 1u);
         }
         ph = __shfl_sync(BRA_FULL, xh[r], 31);
         pl = __shfl_sync(BRA_FULL, s2, 31);
@@ -1094,7 +1128,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
     BRA_CUDA_TRY(cudaMemsetAsync(a.d_fin, 0, nblk, st));
     BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_done, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
     BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_stats_kernel<0><<<grid, EW_THREADS, 0, st>>>(kA, nullptr, a.stride, a.d_period, a.d_done, fcur, nullptr, a.d_tile_last, tiles, a.d_ngroups,
-                                                                                   a.d_tile_heads, a.d_maxgroup, a.d_sumsq));
+                                                                                   a.d_tile_heads, a.d_maxgroup, a.d_sumsq, 0));
     // the ranks themselves are written when (and for the blocks that) a doubling round follows
     const uint8_t* ranks_old     = nullptr;
 
@@ -1169,20 +1203,28 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<2><<<grid, EW_THREADS, 0, st>>>(vA, fcur, ranks_old, a.stride, a.d_period, a.d_done,
                                                                                      a.d_tile_last, tiles, rk, a.d_maxgroup, a.d_sumsq, a.d_ngroups, round_passes, a.d_hist));
         BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_stats_kernel<<<g1, 128, 0, st>>>(a.d_done, a.d_ngroups, a.d_maxgroup, a.d_sumsq, nblk));
-        if (max_n <= BWT_PACK_MAX_N)
+        const bool pack_narrow = max_n <= BWT_PACK_MAX_N;
+        const bool pack_wide   = !pack_narrow && dense && dense_bits <= 20 && max_n <= (1u << 24);
+        if (pack_narrow || pack_wide)
         {
             // packed records: the second sort key travels with the element, the new heads need no gather
-            BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_packed_kernel<<<grid, EW_THREADS, 0, st>>>(vA, rk, fcur, h, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, kB, vB));
+            const uint32_t ks = pack_wide ? BwtPack<true>::KS : BwtPack<false>::KS, vbits = pack_wide ? BwtPack<true>::VBITS : BwtPack<false>::VBITS;
+            if (pack_wide)
+                BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_packed_kernel<true><<<grid, EW_THREADS, 0, st>>>(vA, rk, fcur, h, a.stride, a.d_period, a.d_done, a.d_tile_last,
+                                                                                                       a.d_tile_heads, tiles, kB, vB));
+            else
+                BRA_LAUNCH(P_BWT_PREPARE, st, bwt_dbl_prepare_packed_kernel<false><<<grid, EW_THREADS, 0, st>>>(vA, rk, fcur, h, a.stride, a.d_period, a.d_done, a.d_tile_last,
+                                                                                                        a.d_tile_heads, tiles, kB, vB));
             std::swap(kA, kB);
             std::swap(vA, vB);
             for (uint32_t pass = 0; pass < round_passes; ++pass)
             {
-                if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, pass, BWT_PACK_KEY_SHIFT, a.d_hist, st)) return false;
+                if (!radix_pass_u32(kA, vA, kB, vB, a.stride, a.d_period, a.d_done, max_n, nblk, pass, ks, a.d_hist, st)) return false;
                 std::swap(kA, kB);
                 std::swap(vA, vB);
             }
             BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_stats_kernel<1><<<grid, EW_THREADS, 0, st>>>(kA, vA, a.stride, a.d_period, a.d_done, fnext, vB, a.d_tile_last, tiles, a.d_ngroups,
-                                                                                           a.d_tile_heads, a.d_maxgroup, a.d_sumsq));
+                                                                                           a.d_tile_heads, a.d_maxgroup, a.d_sumsq, vbits));
             std::swap(vA, vB);  // the plain rotation indices
         }
         else
@@ -1199,7 +1241,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             BRA_LAUNCH(P_BWT_HEADS, st, bwt_heads_kernel<1><<<grid, EW_THREADS, 0, st>>>(nullptr, vA, rk, h, a.stride, a.d_period, a.d_done, fcur, fnext, a.d_tile_last, tiles,
                                                               a.d_ngroups, a.d_tile_heads));
         }
-        if (max_n > BWT_PACK_MAX_N)  // (the packed path's head kernel has produced the group statistics already)
+        if (!(pack_narrow || pack_wide))  // (the packed path's head kernel has produced the group statistics already)
             BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vA, fnext, fcur, a.stride, a.d_period, a.d_done, a.d_tile_last, tiles, rk,
                                                                                      a.d_maxgroup, a.d_sumsq, a.d_ngroups, 0, nullptr));
         std::swap(fcur, fnext);
