@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(MTF_WARPS * 32)
                            uint8_t* __restrict__ summ /* [b][seg][256] */, uint16_t* __restrict__ scnt /* [b][seg] */)
 {
     __shared__ int s_last[MTF_WARPS][256];
+    __shared__ int s_lp[MTF_WARPS][256];
     const uint32_t b = blockIdx.y, w = warp_id(), lane = lane_id();
     const uint32_t seg = blockIdx.x * MTF_WARPS + w;
     const uint32_t n   = len[b];
@@ -153,10 +154,23 @@ __global__ void __launch_bounds__(MTF_WARPS * 32)
         mine[k] = last[lane * 8 + k];
         present += mine[k] >= 0;
     }
-    uint32_t rk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int s = 0; s < 256; ++s)
+    // the last occurrences of the PRESENT symbols, compacted (BWT output of text uses a few dozen of the 256): the rank of
+    // a symbol is the number of those that are later than its own
+    int*     lp  = s_lp[w];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
     {
-        const int ls = last[s];  // broadcast read
+        const int      v    = last[r * 32 + lane];
+        const uint32_t ball = __ballot_sync(BRA_FULL, v >= 0);
+        if (v >= 0) lp[cnt + __popc(ball & lanemask_lt())] = v;
+        cnt += __popc(ball);
+    }
+    __syncwarp();
+    uint32_t rk[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (uint32_t s = 0; s < cnt; ++s)
+    {
+        const int ls = lp[s];  // broadcast read
 #pragma unroll
         for (int k = 0; k < 8; ++k) rk[k] += ls > mine[k];
     }
