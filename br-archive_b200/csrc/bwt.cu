@@ -193,8 +193,9 @@ __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t
                                                                    uint32_t cbits, uint32_t* __restrict__ keys, uint32_t npass,
                                                                    uint32_t* __restrict__ ghist)
 {
-    __shared__ uint32_t sh[RS_GHIST_STRIDE];  // digit histograms of every radix pass of the sort that follows
-    __shared__ uint8_t  code[256];
+    __shared__ uint32_t              sh[RS_GHIST_STRIDE];  // digit histograms of every radix pass of the sort that follows
+    __shared__ uint8_t               code[256];
+    __shared__ __align__(16) uint8_t s_code[EW_TILE + 16];  // symbol codes of the tile and of the three symbols behind it
     const uint32_t b = blockIdx.y;
     const uint32_t p = period[b];
     const uint32_t tile0 = blockIdx.x * EW_TILE;
@@ -205,18 +206,64 @@ __global__ void __launch_bounds__(EW_THREADS) bwt_init_keys_kernel(const uint8_t
     const uint8_t* T    = in + (uint64_t) b * stride;
     const uint64_t base = (uint64_t) b * stride;
     const uint32_t tend = min(p, tile0 + EW_TILE);
-    for (uint32_t j = tile0 + threadIdx.x; j < tend; j += EW_THREADS)
+    const uint32_t tn   = tend - tile0;
+    // stage the codes: sixteen symbols per thread (one 128-bit load where the address allows), then the three that follow
+    // the tile -- cyclically, the last tile's wrap to the start of the period
     {
-        uint32_t key = 0;
-        if (j + 3 < p)
-            key = ((uint32_t) code[T[j]] << (3 * cbits)) | ((uint32_t) code[T[j + 1]] << (2 * cbits)) | ((uint32_t) code[T[j + 2]] << cbits) | code[T[j + 3]];
+        const uint32_t i0 = threadIdx.x * 16;
+        uint32_t       w4[4] = {0, 0, 0, 0};
+        if (i0 + 16 <= tn && ((reinterpret_cast<uintptr_t>(T) + tile0 + i0) & 15u) == 0)
+        {
+            const uint4 v = *reinterpret_cast<const uint4*>(T + tile0 + i0);
+            w4[0] = v.x; w4[1] = v.y; w4[2] = v.z; w4[3] = v.w;
+        }
         else
+            for (uint32_t k = 0; k < 16; ++k)
+            {
+                const uint32_t g = i0 + k;  // slot of the staging array: the tile, then three followers, then nothing
+                if (g >= tn + 3) break;
+                uint32_t j = tile0 + g;
+                if (j >= p) j %= p;
+                w4[k >> 2] |= (uint32_t) T[j] << ((k & 3) * 8);
+            }
+        uint32_t c4[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            c4[q] = (uint32_t) code[w4[q] & 0xFFu] | ((uint32_t) code[(w4[q] >> 8) & 0xFFu] << 8) | ((uint32_t) code[(w4[q] >> 16) & 0xFFu] << 16) |
+                    ((uint32_t) code[w4[q] >> 24] << 24);
+        *reinterpret_cast<uint4*>(s_code + i0) = make_uint4(c4[0], c4[1], c4[2], c4[3]);
+        if (threadIdx.x < 3 && tn + threadIdx.x >= EW_TILE)  // (followers behind slot 4095: nobody's sixteen slots reach there)
+        {
+            uint32_t j = tend + threadIdx.x;
+            if (j >= p) j %= p;
+            s_code[tn + threadIdx.x] = code[T[j]];
+        }
+    }
+    __syncthreads();
+    // keys of sixteen consecutive rotations per thread, rolled: key(j+1) = key(j) << cbits | code(j+4), cut to 4 symbols
+    const uint32_t i0 = threadIdx.x * 16;
+    if (i0 < tn)
+    {
+        const uint32_t m    = min(16u, tn - i0);
+        const uint32_t mask = cbits == 8 ? 0xFFFFFFFFu : ((1u << (4 * cbits)) - 1u);
+        uint32_t       key  = ((uint32_t) s_code[i0] << (2 * cbits)) | ((uint32_t) s_code[i0 + 1] << cbits) | s_code[i0 + 2];
+        uint32_t       kk[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k)
+        {
+            key   = ((key << cbits) | s_code[min(i0 + k + 3, tn + 2)]) & mask;
+            kk[k] = key;
+            if ((uint32_t) k < m)
+                for (uint32_t ps = 0; ps < npass; ++ps) atomicAdd(&sh[ps * 256 + ((key >> (8 * ps)) & 0xFFu)], 1u);
+        }
+        uint32_t* ko = keys + base + tile0 + i0;
+        if (m == 16 && (reinterpret_cast<uintptr_t>(ko) & 15u) == 0)
         {
 #pragma unroll
-            for (int d = 0; d < 4; ++d) key = (key << cbits) | code[T[(j + d) % p]];
+            for (int q = 0; q < 4; ++q) reinterpret_cast<uint4*>(ko)[q] = make_uint4(kk[4 * q], kk[4 * q + 1], kk[4 * q + 2], kk[4 * q + 3]);
         }
-        keys[base + j] = key;
-        for (uint32_t ps = 0; ps < npass; ++ps) atomicAdd(&sh[ps * 256 + ((key >> (8 * ps)) & 0xFFu)], 1u);
+        else
+            for (uint32_t k = 0; k < m; ++k) ko[k] = kk[k];
     }
     __syncthreads();
     for (uint32_t i = threadIdx.x; i < npass * 256; i += EW_THREADS)
