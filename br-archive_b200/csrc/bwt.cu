@@ -1395,7 +1395,8 @@ __device__ __forceinline__ uint32_t ib_walkers(uint32_t K, const uint32_t* __res
 // Assemble the output from the scratch rows. A warp takes 32 consecutive walkers: every lane fetches the record of one
 // (offset, length: two coalesced loads instead of a chain of dependent ones per walker), then the warp copies the rows
 // one after the other, a row being a few aligned 32-bit words per lane.
-__device__ __forceinline__ void ibwt_copy_row(const uint8_t* __restrict__ row, uint8_t* __restrict__ dst, uint32_t m, uint32_t l)
+// `l` of `nl` lanes copy one row
+__device__ __forceinline__ void ibwt_copy_row(const uint8_t* __restrict__ row, uint8_t* __restrict__ dst, uint32_t m, uint32_t l, uint32_t nl)
 {
     // aligned 32-bit stores: the row is 16-byte aligned, the destination is not -- every lane funnels the two row words
     // that straddle its output word together; the few bytes before the first and after the last whole word go singly
@@ -1404,7 +1405,7 @@ __device__ __forceinline__ void ibwt_copy_row(const uint8_t* __restrict__ row, u
     const uint32_t  nw    = (m - mis) >> 2;
     const uint32_t* row32 = reinterpret_cast<const uint32_t*>(row);
     uint32_t*       dst32 = reinterpret_cast<uint32_t*>(dst + mis);
-    for (uint32_t k = l; k < nw; k += 32)
+    for (uint32_t k = l; k < nw; k += nl)
     {
         const uint32_t sb = mis + 4u * k;
         const uint32_t w0 = row32[sb >> 2];
@@ -1436,11 +1437,13 @@ __global__ void __launch_bounds__(256)
         if (my_steps > cap) my_off = IB_INVALID;  // did not fit: the emit walk does it
     }
     uint8_t* ob = out + (uint64_t) b * stride;
-    for (uint32_t i = 0; i < 32; ++i)
+    // walks are about R bytes long: with short rows (R = 64: sixteen words) the two halves of the warp copy one row each
+    const uint32_t nl = R <= 64 ? 16u : 32u, per = 32u / nl, sub = l % nl, grp = l / nl;
+    for (uint32_t i = 0; i < 32; i += per)
     {
-        const uint32_t o0 = __shfl_sync(BRA_FULL, my_off, i), steps = __shfl_sync(BRA_FULL, my_steps, i);
+        const uint32_t o0 = __shfl_sync(BRA_FULL, my_off, i + grp), steps = __shfl_sync(BRA_FULL, my_steps, i + grp);
         if (o0 == IB_INVALID) continue;
-        ibwt_copy_row(tmp + ((uint64_t) b * kmax + w0 + i) * cap, ob + o0, min(steps, n - min(n, o0)), l);
+        ibwt_copy_row(tmp + ((uint64_t) b * kmax + w0 + i + grp) * cap, ob + o0, min(steps, n - min(n, o0)), sub, nl);
     }
 }
 
