@@ -6,12 +6,15 @@
 //   sort). Here the same order is built as a suffix array of the cyclic string:
 //     1. period detection: the smallest p | n with T[i] == T[(i+p) mod n]. Rotations i and i+p
 //        are identical, so it suffices to sort the p rotations of the primitive root (all
-//        distinct) and replicate each n/p times in ascending index -- exactly the tie rule.
-//     2. 4-byte keys + 4 LSD radix passes (sort.cu) order the rotations by their first 4 bytes.
+//        distinct) and replicate each n/p times in ascending index -- exactly the tie rule. A 32-byte pretest refutes
+//        the divisors; only a block with a surviving candidate compares itself with its shift, one candidate per round.
+//     2. keys of the first 4 symbols (dense per-block symbol codes) + 2-4 LSD radix passes (sort.cu).
 //     3. prefix doubling, Manber-Myers style: walking the current order j = 0..p-1, rotation
 //        SA[j]-h is appended to its own h-group, which a stable radix sort on rank[SA[j]-h]
-//        does in 2-3 passes; new group heads give the 2h-ranks. Repeats until every group is a
-//        singleton (all rotations of a primitive string differ, so this terminates with h < 2p).
+//        does in 1-3 passes; new group heads give the 2h-ranks. Where the fields fit 64 bits the sort moves packed
+//        records (key, group of the traversal slot, rotation): the new heads are then a neighbour compare, no gather.
+//        Repeats until every group is a singleton (all rotations of a primitive string differ, so this terminates with
+//        h < 2p); blocks whose remaining groups are small are finished by direct comparison of the rotations.
 //     4. gather L[j] = T[SA[j/k] - 1], primary = k * (row of rotation 0), k = n/p.
 //
 // INVERSE (replaces reference bra_bwt_decode2, bra_bwt.c:133-168)
@@ -19,8 +22,9 @@
 //   as W[j] = transform[j] << 8 | F[j] so that the chase needs one load per output byte. The
 //   n-step dependent chase is cut into ~n/R independent walks (16384 per block: twice the walkers halve the blocks whose W
 //   arrays are in flight at once, and with them the DRAM sectors fetched per step) that start at every R-th row
-//   (and at the primary row) and stop at the next start row; a per-block stitch orders the
-//   walks from the primary row and a second walk writes the bytes at their final offsets.
+//   (and at the primary row) and stop at the next start row, keeping their bytes in scratch rows (a walk that fills its
+//   row continues as an overflow walker); a per-block stitch orders the walks from the primary row by pointer doubling
+//   and a copy kernel assembles the output. Periodic blocks write their orbit once and replicate it.
 #include "bra_common.cuh"
 #include "bra_hd.h"
 #include "bra_kernels.h"

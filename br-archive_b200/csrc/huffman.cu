@@ -11,15 +11,19 @@
 //                tile its first output bit (and the block its encoded_size).
 //   pack       : each thread owns 16 consecutive symbols, an exclusive prefix sum over code
 //                lengths gives its bit offset; codewords are OR-ed MSB-first into a shared-memory
-//                image of the tile's output words, which then leaves with coalesced word stores
-//                (the two words shared with neighbouring tiles by atomicOr).
+//                image of the tile's output words, which then leaves with plain coalesced word stores: a tile owns
+//                every word it starts in (the bits of the preceding codes that share its first word are re-derived
+//                by walking back over at most 32 symbols), so there is no payload memset and no global atomic.
 // DECODE (the format has no sync markers: bra_huffman_t is lengths + two sizes, lib_bra_types.h:51-56)
-//   Self-synchronising decode: the payload is cut into 128-bit subsequences, one per thread,
+//   Self-synchronising decode: the payload is cut into 1024-bit subsequences, one per thread,
 //   256 per CTA. Every thread decodes from its current guess of where the first codeword of
 //   its subsequence starts and publishes where it crossed into the next subsequence; guesses
 //   are refined by fixed-point iteration (in shared memory inside the CTA, across CTAs by
 //   re-launching while any CTA's entry changed). Subsequence 0 starts at bit 0, so the fixed
 //   point is the true parse. Symbol counts are scanned and a second pass writes the output.
+//   Codes that hardly ever re-synchronise (at most 12 bits, nearly uniform length: incompressible data) take the
+//   phase mode instead: every subsequence is walked once from each of its max_len possible starts, and the maps
+//   start -> (next start, codewords) are chained per sequence and per block (see HD_PHASE_MAX).
 #include "bra_common.cuh"
 #include "bra_hd.h"
 #include "bra_kernels.h"

@@ -1,8 +1,8 @@
 // sort.cu -- batched, segmented, stable LSD radix-sort pass, one sweep per digit (8-bit digits).
 //
 // Used three ways on the hot path:
-//   * forward BWT: initial sort of rotation indices by their first symbols (4-5 passes) and the
-//     per-doubling-round stable re-bucketing by rank (2-3 passes) -- replaces the qsort_r call of
+//   * forward BWT: initial sort of rotation indices by their first 4 symbols (2-4 passes) and the
+//     per-doubling-round stable re-bucketing by rank (1-3 passes) -- replaces the qsort_r call of
 //     reference src/encoders/bra_bwt.c:91. (A 10-bit digit, 2 passes per round, was measured in round 1: the wider
 //     shared-memory counters and 4-element output runs make each pass ~1.7x slower, a net loss.)
 //   * inverse BWT: one 8-bit pass with the BWT bytes as keys builds `transform[]`, i.e. the stable
@@ -12,14 +12,16 @@
 //   * The digit histogram of each block (256 counters) is produced beforehand by whoever writes the keys (all digits of
 //     a sort at once), so no pass re-reads its keys to count them.
 //   * Each CTA takes a tile of 4096 elements by ticket (an atomic counter: a tile only ever waits for tiles with smaller
-//     tickets, which are running or finished, so the waits cannot deadlock whatever the launch order), ranks its
-//     elements stably with warp match + per-warp counters, and obtains the number of equal digits in the earlier tiles of
-//     its block by decoupled look-back over per-tile status words (count | flag | pass tag in one 32-bit word).
+//     tickets, which are running or finished, so the waits cannot deadlock whatever the launch order; the tickets of up to
+//     64 blocks are interleaved, so that a tile's predecessors in its own block are many tickets old and have usually
+//     published their inclusive counts), ranks its elements stably per warp -- match.any, or lane bits OR-ed into
+//     shared-memory words per digit when the warp's digits are diverse -- and obtains the number of equal digits in the
+//     earlier tiles of its block by decoupled look-back over per-tile status words (count | flag in one 32-bit word).
 //   * The tile is reordered in shared memory so that each digit's run leaves the SM as one contiguous store.
 //   * The values of a tile are not needed before the reorder: they are fetched by one bulk-asynchronous copy (TMA,
 //     cp.async.bulk + mbarrier) issued when the CTA starts and land in shared memory while the ranking runs.
 // Algorithmic traffic per pass and element: 16 bytes (u32 key + value, read + write). HBM/L2 bound in bytes, issue
-// bound in practice (ranking); no tensor-core work.
+// and shared-memory bound in practice (ranking, reorder); no tensor-core work.
 #include "bra_common.cuh"
 #include "bra_kernels.h"
 
