@@ -1214,8 +1214,7 @@ bool bwt_forward_batch(const BwtFwdArgs& a, cudaStream_t st)
             BRA_LAUNCH(P_BWT_MISC, st, bwt_reset_tile_last_kernel<<<dim3(bra_div_up(tiles, 256), nblk), 256, 0, st>>>(a.d_finskip, a.d_tile_last, tiles));
             BRA_LAUNCH(P_BWT_FINISH, st, bwt_finish_kernel<<<grid, EW_THREADS, 0, st>>>(a.d_in, a.stride, a.d_period, a.d_finskip, h, vA, fcur, vB, fnext,
                                                                                      a.d_tile_last, tiles, a.d_ngroups));
-            BRA_LAUNCH(P_BWT_RANKS, st, bwt_ranks_kernel<1><<<grid, EW_THREADS, 0, st>>>(vB, fnext, fcur, a.stride, a.d_period, a.d_finskip, a.d_tile_last, tiles, rk,
-                                                                                  a.d_maxgroup, a.d_sumsq, a.d_ngroups, 0, nullptr));
+            // (no group statistics afterwards: they only feed the decision to try the finisher, which a block gets once)
             if (stat[1] == stat[0])
             {
                 // every block still sorting went through the finisher: its outputs simply become the current buffers
